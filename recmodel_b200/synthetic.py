@@ -1,0 +1,101 @@
+"""Seeded synthetic implicit-feedback matrices.
+
+The reference ships no data (its notebook loads a Netflix.npz that is not in the
+repository), so every parity test and bench line in this repo runs on matrices from
+this generator: distinct (user, item) pairs, item popularity ~ rank^-0.8, log-normal
+user activity, integer counts 1..5 stored as float32, indices sorted per row. An
+optional planted low-rank structure makes Recall@N meaningfully above chance.
+
+Shapes of BASELINE.json's configs are in ``SHAPES``.
+"""
+import numpy as np
+import scipy.sparse
+
+DEFAULT_SEED = 20240229
+
+SHAPES = {
+    # name: (users, items, nnz, dim, bias)
+    "cfg1": (6040, 3706, 1_000_000, 64, True),      # ML-1M shape, CPU-reference config
+    "cfg2": (138_493, 26_744, 20_000_000, 128, False),  # ML-20M shape, 1 B200
+    "cfg3": (480_189, 17_770, 100_000_000, 128, False),  # Netflix shape
+    "cfg4": (10_000_000, 1_000_000, 1_000_000_000, 256, False),
+}
+
+
+def _popularity(n_items, exponent, rng):
+    w = np.arange(1, n_items + 1, dtype=np.float64) ** (-exponent)
+    rng.shuffle(w)  # popular items are not the low ids
+    return w / w.sum()
+
+
+def make_counts(n_users, n_items, nnz, seed=DEFAULT_SEED, planted_rank=0, exponent=0.8,
+                sigma=1.0, max_row_frac=0.5):
+    """CSR float32 count matrix with exactly ``nnz`` distinct entries (or slightly fewer if
+    the shape cannot hold them). Deterministic in ``seed``."""
+    rng = np.random.default_rng(seed)
+    nnz = int(min(nnz, int(n_users * n_items * max_row_frac)))
+    act = rng.lognormal(mean=0.0, sigma=sigma, size=n_users)
+    act /= act.sum()
+    pop = _popularity(n_items, exponent, rng)
+    cum_u = np.cumsum(act)
+    cum_u[-1] = 1.0
+    cum_i = np.cumsum(pop)
+    cum_i[-1] = 1.0
+
+    if planted_rank > 0:
+        # users and items get a cluster; a user draws most items from its own cluster
+        ucl = rng.integers(0, planted_rank, size=n_users)
+        icl = rng.integers(0, planted_rank, size=n_items)
+        order = np.argsort(icl, kind="stable")
+        starts = np.searchsorted(icl[order], np.arange(planted_rank + 1))
+
+    keys = np.empty(0, dtype=np.int64)
+    want = nnz
+    rounds = 0
+    while keys.size < nnz and rounds < 30:
+        m = int((want - keys.size) * 1.25) + 1024
+        u = np.searchsorted(cum_u, rng.random(m), side="right").astype(np.int64)
+        i = np.searchsorted(cum_i, rng.random(m), side="right").astype(np.int64)
+        if planted_rank > 0:
+            own = rng.random(m) < 0.8
+            c = ucl[u]
+            lo = starts[c]
+            span = np.maximum(starts[c + 1] - lo, 1)
+            inside = order[np.minimum(lo + (rng.random(m) * span).astype(np.int64), n_items - 1)]
+            i = np.where(own, inside, i)
+        np.minimum(u, n_users - 1, out=u)
+        np.minimum(i, n_items - 1, out=i)
+        keys = np.unique(np.concatenate([keys, u * n_items + i]))
+        rounds += 1
+    if keys.size > nnz:
+        drop = rng.choice(keys.size, size=keys.size - nnz, replace=False)
+        mask = np.ones(keys.size, dtype=bool)
+        mask[drop] = False
+        keys = keys[mask]
+    rows = (keys // n_items).astype(np.int64)
+    cols = (keys % n_items).astype(np.int32)
+    vals = rng.integers(1, 6, size=keys.size).astype(np.float32)
+    indptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=n_users), out=indptr[1:])
+    idx_dtype = np.int32 if keys.size < 2**31 - 1 else np.int64
+    mat = scipy.sparse.csr_matrix((vals, cols, indptr.astype(idx_dtype)), shape=(n_users, n_items))
+    mat.has_sorted_indices = True  # keys are sorted, so columns ascend inside each row
+    return mat
+
+
+def split_train_test(matrix, train=0.8, seed=1993):
+    """Copy-safe restatement of the reference's split (/root/reference/RecModel/utils.py:19-35):
+    ``np.random.seed(seed)``; entry k (CSR data order) goes to train iff ``rand(nnz)[k] < train``.
+    The reference aliases both halves under SciPy >= 1.15 and returns
+    empty matrices; this version keeps its RNG semantics and fixes the aliasing."""
+    matrix = matrix.tocsr()
+    np.random.seed(seed)
+    is_train = np.random.rand(len(matrix.data)) < train
+    out = []
+    for keep in (is_train, ~is_train):
+        coo = matrix.tocoo(copy=True)
+        coo.data = np.where(keep, coo.data, 0).astype(matrix.dtype)
+        part = coo.tocsr()
+        part.eliminate_zeros()
+        out.append(part)
+    return out
