@@ -1,0 +1,121 @@
+/* libwmf_b200.so - C ABI of the B200-native WMF (implicit-feedback ALS) train + top-N path.
+ *
+ * The reference (titoeb/RecModel) has no FFI, plugin or operator registry on this path: the
+ * whole of WMF is NumPy/SciPy Python (RecModel/wmf_model.py:1-6). The drop-in
+ * boundary is therefore the Python class `WMF`; these entry points are what a maintainer would
+ * bind from that class with ctypes, one per NumPy/LAPACK call site the
+ * kernels replace. Each declaration cites the reference lines it stands in for, relative to
+ * /root/reference/.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless the name ends in _host. The caller owns every
+ *    buffer; the library allocates nothing persistent.
+ *  - `stream` is a cudaStream_t passed as void*. All work is stream-ordered, no hidden syncs.
+ *  - Factor matrices are row-major float32 with leading dimension ld (elements).
+ *  - CSR: indptr int64[rows+1], indices int32[nnz], data float32[nnz].
+ *  - Return 0 on success; non-zero = error, text from wmf_last_error() (thread-local).
+ *  - sm_100a only. There is no CPU path: on a machine without a B200-class device every
+ *    compute entry point returns WMF_ERR_NO_DEVICE.
+ */
+#ifndef WMF_B200_H
+#define WMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WMF_OK 0
+#define WMF_ERR_INVALID 1     /* bad argument (null pointer, f out of range, ...) */
+#define WMF_ERR_WORKSPACE 2   /* workspace too small: ask wmf_*_workspace_bytes */
+#define WMF_ERR_CUDA 3        /* CUDA runtime error, see wmf_last_error */
+#define WMF_ERR_NO_DEVICE 4   /* no sm_100 device visible */
+#define WMF_ERR_UNSUPPORTED 5 /* shape outside what the selected algorithm handles */
+
+#define WMF_MAX_F 320 /* largest factor width (dim, +1 with bias) any kernel accepts */
+
+/* Half-step algorithm selector */
+#define WMF_ALGO_AUTO 0
+#define WMF_ALGO_SIMT 1    /* FP32 CUDA-core Gram + Cholesky/LU; any f <= WMF_MAX_F; accuracy reference */
+#define WMF_ALGO_TCGEN05 2 /* 3xTF32 tcgen05 Gram in TMEM + FP32 solve; dim in {64,128} */
+
+/* Count preprocessing modes */
+#define WMF_PREPROCESS_LOG 0    /* d = alpha*log(1+beta*x)   wmf_model.py:120 */
+#define WMF_PREPROCESS_LINEAR 1 /* d = alpha*x               wmf_model.py:123 */
+
+const char* wmf_last_error(void);
+int wmf_version(void);
+/* 0 if a usable sm_100 device is current, else WMF_ERR_NO_DEVICE. Fills sm_count if non-null. */
+int wmf_device_check(int* sm_count);
+
+/* K6. In-place count preprocessing.                      replaces wmf_model.py:66-70,119-123 */
+int wmf_preprocess(float* data, int64_t nnz, int mode, float alpha, float beta, void* stream);
+
+/* K1. G = Y^T Y + lambda*I  (f x f, row-major, ld = f).  replaces np.dot(Y.T,Y)+lambda*eye at
+ * wmf_model.py:215,244,258,332 (and the Gram inside :85,:88). ones_col0 != 0 computes with
+ * column 0 of Y replaced by 1 (the bias path's Y[:,0] = 1, :331) without touching Y.
+ * Deterministic: per-CTA partials in `ws`, reduced in a fixed order. */
+size_t wmf_gram_workspace_bytes(int64_t n, int f);
+int wmf_gram(const float* Y, int64_t n, int f, int64_t ldy, float lambda, int ones_col0,
+             float* G, void* ws, size_t ws_bytes, void* stream);
+
+/* K2. One ALS half-step over `rows` CSR rows:            replaces the row loops at
+ * wmf_model.py:220-239 (recompute_factors), :337-350 (recompute_factors_bias) and the Pool
+ * variants :242-309.
+ *   x_r = (G + sum_j d_j y_j y_j^T)^-1  sum_j (d_j+1) y_j ,   j over the stored entries of row r
+ * bias != 0: y_j has column 0 replaced by 1 and d_j = data_j - Y[j*ldy+0] (:328-343); G must
+ * then come from wmf_gram(..., ones_col0=1). Rows with no entries give the zero vector
+ * (:223-225; with bias solve(G,0)=0 is the same). `row_order` (nullable) is a permutation of
+ * [0,rows) giving the processing order (longest rows first balances the power-law tail); it
+ * does not change any row's arithmetic. X row r is written at X + r*ldx. */
+size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo);
+/* 1 if `algo` (WMF_ALGO_SIMT / WMF_ALGO_TCGEN05) handles factor width f with/without bias, else 0. */
+int wmf_als_half_step_supports(int algo, int f, int bias);
+int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data,
+                      int64_t rows, const int32_t* row_order, const float* Y, int64_t ldy, int f,
+                      const float* G, int bias, float* X, int64_t ldx, int algo, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* K3. Fused prediction + error reduction over the non-zero stored entries of a CSR matrix:
+ * replaces predict + eval_prec (wmf_model.py:205-211, base_model.py:163-176).
+ * Each prediction is computed in NumPy's rounding order (products rounded, pairwise reduce,
+ * then + user bias + item bias). out[0] = sum (r-yhat)^2, out[1] = sum |r-yhat|, out[2] = count
+ * (doubles; entries whose stored value is 0 are skipped like nonzero() does). Deterministic. */
+size_t wmf_sddmm_loss_workspace_bytes(int64_t nnz);
+int wmf_sddmm_loss(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows,
+                   int64_t nnz, const float* U, int64_t ldu, const float* V, int64_t ldv, int f, int bias,
+                   double* out3, void* ws, size_t ws_bytes, void* stream);
+
+/* R8. Element-wise pair scores, bit-exact with NumPy:    replaces WMF.predict (:191-211).
+ * users/items are int64 index arrays of length n; user_stride 0 broadcasts a single user. */
+int wmf_predict_pairs(const int64_t* users, int64_t user_stride, const int64_t* items, int64_t n,
+                      const float* U, int64_t ldu, const float* V, int64_t ldv, int f, int bias,
+                      float* out, void* stream);
+
+/* K4+K5. Top-N over a candidate list for a batch of users: replaces WMF.rank (:25-47).
+ * Scores are the bit-exact fp32 scores of wmf_predict_pairs, so the selected index SET equals
+ * the reference's; order is descending score, ties broken by lower candidate position.
+ * cand (nullable) = int64 candidate item ids [ni] (null: items 0..ni-1). out_ids [nu*topn]
+ * receives item ids, out_scores (nullable) their scores. */
+size_t wmf_score_topk_workspace_bytes(int64_t nu, int64_t ni, int topn);
+int wmf_score_topk(const int64_t* users, int64_t nu, const int64_t* cand, int64_t ni, const float* U,
+                   int64_t ldu, const float* V, int64_t ldv, int f, int bias, int topn, int64_t* out_ids,
+                   float* out_scores, void* ws, size_t ws_bytes, void* stream);
+
+/* K7. Unweighted half-step X = R * (Ginv * Y^T)^T:       replaces wmf_model.py:85,:88.
+ * wmf_inverse: Ginv = inv(G) for a small dense f x f matrix (np.linalg.inv), one CTA.
+ * wmf_dense_right_multiply: W[n x f] = Y[n x f] * M[f x f]^T   (= (M Y^T)^T).
+ * wmf_spmm: X[r] = sum_j data_j * W[indices_j]                 (csr_matrix.dot). */
+int wmf_inverse(const float* G, int f, float* Ginv, void* ws, size_t ws_bytes, void* stream);
+size_t wmf_inverse_workspace_bytes(int f);
+int wmf_dense_right_multiply(const float* Y, int64_t n, int64_t ldy, const float* M, int f, float* W,
+                             int64_t ldw, void* stream);
+int wmf_spmm(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows,
+             const float* W, int64_t ldw, int f, float* X, int64_t ldx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMF_B200_H */

@@ -1,0 +1,56 @@
+// wmf_als_half_step: argument checks and algorithm dispatch (SIMT reference path /
+// tcgen05 path).
+#include "common.cuh"
+#include "half_step.cuh"
+
+using namespace wmf;
+
+static int resolve_algo(int algo, int f, int bias) {
+    if (algo == WMF_ALGO_AUTO) return tc_half_step_supported(f, bias) ? WMF_ALGO_TCGEN05 : WMF_ALGO_SIMT;
+    return algo;
+}
+
+extern "C" {
+
+int wmf_als_half_step_supports(int algo, int f, int bias) {
+    if (f <= 0 || f > WMF_MAX_F || (bias && f < 2)) return 0;
+    if (algo == WMF_ALGO_TCGEN05) return tc_half_step_supported(f, bias) ? 1 : 0;
+    return (algo == WMF_ALGO_SIMT || algo == WMF_ALGO_AUTO) ? 1 : 0;
+}
+
+size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo) {
+    if (f <= 0 || f > WMF_MAX_F) return 0;
+    size_t a = simt_half_step_workspace_bytes(f);
+    size_t b = 0;
+    if (algo != WMF_ALGO_SIMT) {
+        size_t b0 = tc_half_step_supported(f, 0) ? tc_half_step_workspace_bytes(rows, f, 0) : 0;
+        size_t b1 = tc_half_step_supported(f, 1) ? tc_half_step_workspace_bytes(rows, f, 1) : 0;
+        b = b0 > b1 ? b0 : b1;
+    }
+    return a > b ? a : b;
+}
+
+int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows,
+                      const int32_t* row_order, const float* Y, int64_t ldy, int f, const float* G, int bias,
+                      float* X, int64_t ldx, int algo, void* ws, size_t ws_bytes, void* stream) {
+    WMF_REQUIRE(f > 0 && f <= WMF_MAX_F && (!bias || f >= 2), "wmf_als_half_step: f=%d outside 1..%d", f, WMF_MAX_F);
+    WMF_REQUIRE(rows >= 0 && rows < (1ll << 31), "wmf_als_half_step: rows=%lld out of range", (long long)rows);
+    if (rows == 0) return WMF_OK;
+    WMF_REQUIRE(indptr && Y && G && X && ldy >= f && ldx >= f, "wmf_als_half_step: null pointer or short leading dimension");
+    WMF_REQUIRE(algo == WMF_ALGO_AUTO || algo == WMF_ALGO_SIMT || algo == WMF_ALGO_TCGEN05,
+                "wmf_als_half_step: unknown algo %d", algo);
+    const int chosen = resolve_algo(algo, f, bias);
+    HalfStepParams p{};
+    p.indptr = indptr; p.indices = indices; p.data = data; p.rows = rows; p.row_order = row_order;
+    p.Y = Y; p.ldy = ldy; p.f = f; p.G = G; p.bias = bias; p.X = X; p.ldx = ldx;
+    if (chosen == WMF_ALGO_TCGEN05) {
+        if (!tc_half_step_supported(f, bias)) {
+            set_error("wmf_als_half_step: tcgen05 path takes dim in {64,128} (f=%d, bias=%d)", f, bias);
+            return WMF_ERR_UNSUPPORTED;
+        }
+        return tc_half_step(p, ws, ws_bytes, (cudaStream_t)stream);
+    }
+    return simt_half_step(p, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""Device-side operations of the WMF path: thin wrappers that hand torch CUDA tensors
+(device memory + stream only) to the C-ABI kernels of libwmf_b200.so.
+
+Nothing in this module computes on the host or with torch operators on the hot path; torch is
+used for allocation, H2D/D2H copies, the current stream, and (in ``DeviceCSR.transpose``) a
+stable device sort for the one-off CSR transpose.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+_workspaces = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def workspace(nbytes, device):
+    """A cached, grow-only scratch buffer per device. Kernels launched back to back on one
+    stream may share it (stream order serialises them)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise _lib.WMFLibraryError("recmodel_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_cuda and t.stride(-1) == 1, "expected a row-major float32 CUDA tensor"
+    return t
+
+
+class DeviceCSR:
+    """CSR matrix resident in HBM: indptr int64[rows+1], indices int32[nnz], data float32[nnz],
+    plus ``row_order`` (int32 permutation, longest rows first) used as the processing order of
+    the half-step kernels."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data = indptr, indices, data
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(indices.numel())
+        self._row_order = None
+
+    @classmethod
+    def from_scipy(cls, mat, device=None):
+        device = device or default_device()
+        mat = mat.tocsr()
+        if mat.shape[1] >= 2 ** 31:
+            raise ValueError("column count must fit int32")
+        indptr = torch.from_numpy(np.ascontiguousarray(mat.indptr, dtype=np.int64)).to(device, non_blocking=True)
+        indices = torch.from_numpy(np.ascontiguousarray(mat.indices, dtype=np.int32)).to(device, non_blocking=True)
+        data = torch.from_numpy(np.ascontiguousarray(mat.data, dtype=np.float32)).to(device, non_blocking=True)
+        return cls(indptr, indices, data, mat.shape)
+
+    @property
+    def device(self):
+        return self.indptr.device
+
+    @property
+    def row_order(self):
+        if self._row_order is None:
+            counts = self.indptr[1:] - self.indptr[:-1]
+            self._row_order = torch.sort(counts, descending=True, stable=True).indices.to(torch.int32)
+        return self._row_order
+
+    def with_data(self, data):
+        out = DeviceCSR(self.indptr, self.indices, data, self.shape)
+        out._row_order = self._row_order
+        return out
+
+    def row_ids(self):
+        counts = self.indptr[1:] - self.indptr[:-1]
+        return torch.repeat_interleave(torch.arange(self.shape[0], device=self.device, dtype=torch.int32), counts,
+                                       output_size=self.nnz)
+
+    def transpose(self):
+        """CSR of the transpose with ascending row ids inside every output row: the ordering
+        ``count_mat.T.tocsr()`` produces (wmf_model.py:128). One stable device sort by column."""
+        rows, cols = self.shape
+        perm = torch.sort(self.indices, stable=True).indices
+        out_indices = self.row_ids()[perm]
+        out_data = self.data[perm]
+        counts = torch.bincount(self.indices, minlength=cols)
+        out_indptr = torch.zeros(cols + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=out_indptr[1:])
+        return DeviceCSR(out_indptr, out_indices.contiguous(), out_data.contiguous(), (cols, rows))
+
+    def row_slice(self, r0, r1):
+        """Rows [r0, r1) as an independent DeviceCSR (used to shard rows across GPUs)."""
+        lo, hi = int(self.indptr[r0].item()), int(self.indptr[r1].item())
+        return DeviceCSR((self.indptr[r0:r1 + 1] - lo).contiguous(), self.indices[lo:hi], self.data[lo:hi],
+                         (r1 - r0, self.shape[1]))
+
+    def to_scipy(self):
+        import scipy.sparse
+        return scipy.sparse.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                                       shape=self.shape)
+
+
+def preprocess_(data, mode, alpha, beta):
+    """In place d = alpha*log(1+beta*x) | alpha*x  (wmf_model.py:119-123)."""
+    lib = _lib.load()
+    codes = {"log": _lib.PREPROCESS_LOG, "linear": _lib.PREPROCESS_LINEAR}
+    if mode not in codes:
+        raise ValueError(f"Pre_process_count {mode} is not implement please use log or linear.")
+    _lib.check(lib.wmf_preprocess(_ptr(_f32(data)), data.numel(), codes[mode], float(alpha), float(beta), _stream()),
+               "wmf_preprocess")
+    return data
+
+
+def gram(Y, lam, ones_col0=False):
+    """G = Y^T Y + lam I (wmf_model.py:215 / :332 with the ones column)."""
+    lib = _lib.load()
+    _f32(Y)
+    n, f = Y.shape
+    G = torch.empty((f, f), dtype=torch.float32, device=Y.device)
+    need = lib.wmf_gram_workspace_bytes(n, f)
+    ws = workspace(need, Y.device)
+    _lib.check(lib.wmf_gram(_ptr(Y), n, f, Y.stride(0), float(lam), int(bool(ones_col0)), _ptr(G), _ptr(ws),
+                            ws.numel(), _stream()), "wmf_gram")
+    return G
+
+
+def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_order=True):
+    """X = one ALS half-step over the rows of ``csr`` against fixed factors Y
+    (wmf_model.py:213-240 / :311-351)."""
+    lib = _lib.load()
+    _f32(Y)
+    _f32(G)
+    rows = csr.shape[0]
+    f = Y.shape[1]
+    if csr.shape[1] != Y.shape[0]:
+        raise ValueError(f"count matrix has {csr.shape[1]} columns but Y has {Y.shape[0]} rows")
+    X = out if out is not None else torch.empty((rows, f), dtype=torch.float32, device=Y.device)
+    need = lib.wmf_als_half_step_workspace_bytes(rows, f, algo)
+    ws = workspace(need, Y.device)
+    order = csr.row_order if use_row_order else None
+    _lib.check(lib.wmf_als_half_step(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), rows, _ptr(order), _ptr(Y),
+                                     Y.stride(0), f, _ptr(G), int(bool(bias)), _ptr(X), X.stride(0), int(algo),
+                                     _ptr(ws), ws.numel(), _stream()), "wmf_als_half_step")
+    return X
+
+
+def sddmm_loss(csr, U, V, bias=False):
+    """Device tensor [sum sq err, sum abs err, count] (float64) over the non-zero stored entries
+    of ``csr`` (base_model.py:163-176 with predict, wmf_model.py:205-211)."""
+    lib = _lib.load()
+    _f32(U)
+    _f32(V)
+    out = torch.empty(3, dtype=torch.float64, device=U.device)
+    need = lib.wmf_sddmm_loss_workspace_bytes(csr.nnz)
+    ws = workspace(need, U.device)
+    _lib.check(lib.wmf_sddmm_loss(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), csr.shape[0], csr.nnz, _ptr(U),
+                                  U.stride(0), _ptr(V), V.stride(0), U.shape[1], int(bool(bias)), _ptr(out), _ptr(ws),
+                                  ws.numel(), _stream()), "wmf_sddmm_loss")
+    return out
+
+
+def predict_pairs(users, items, U, V, bias=False):
+    """float32 scores of (users[k], items[k]); a single user broadcasts (wmf_model.py:191-211)."""
+    lib = _lib.load()
+    _f32(U)
+    _f32(V)
+    n = items.numel()
+    stride = 1
+    if users.numel() == 1 and n != 1:
+        stride = 0
+    elif users.numel() != n:
+        raise ValueError("users and items need to have the same length or only one user / item needs to be provided.")
+    out = torch.empty(n, dtype=torch.float32, device=U.device)
+    _lib.check(lib.wmf_predict_pairs(_ptr(users), stride, _ptr(items), n, _ptr(U), U.stride(0), _ptr(V), V.stride(0),
+                                     U.shape[1], int(bool(bias)), _ptr(out), _stream()), "wmf_predict_pairs")
+    return out
+
+
+def score_topk(users, cand, U, V, topn, bias=False, want_scores=False):
+    """Top-``topn`` candidate ids [nu x topn] (int64), best first, for each user in ``users``
+    over the shared candidate list ``cand`` (None = all items) (wmf_model.py:25-47)."""
+    lib = _lib.load()
+    _f32(U)
+    _f32(V)
+    nu = users.numel()
+    ni = V.shape[0] if cand is None else cand.numel()
+    ids = torch.empty((nu, topn), dtype=torch.int64, device=U.device)
+    scores = torch.empty((nu, topn), dtype=torch.float32, device=U.device) if want_scores else None
+    need = lib.wmf_score_topk_workspace_bytes(nu, ni, topn)
+    ws = workspace(need, U.device)
+    _lib.check(lib.wmf_score_topk(_ptr(users), nu, _ptr(cand), ni, _ptr(U), U.stride(0), _ptr(V), V.stride(0),
+                                  U.shape[1], int(bool(bias)), int(topn), _ptr(ids), _ptr(scores), _ptr(ws), ws.numel(),
+                                  _stream()), "wmf_score_topk")
+    return (ids, scores) if want_scores else ids
+
+
+def unweighted_half_step(csr, Y, lam):
+    """X = R (inv(Y^T Y + lam I) Y^T)^T  (wmf_model.py:85 / :88)."""
+    lib = _lib.load()
+    _f32(Y)
+    n, f = Y.shape
+    G = gram(Y, lam)
+    Ginv = torch.empty_like(G)
+    ws = workspace(lib.wmf_inverse_workspace_bytes(f), Y.device)
+    _lib.check(lib.wmf_inverse(_ptr(G), f, _ptr(Ginv), _ptr(ws), ws.numel(), _stream()), "wmf_inverse")
+    W = torch.empty((n, f), dtype=torch.float32, device=Y.device)
+    _lib.check(lib.wmf_dense_right_multiply(_ptr(Y), n, Y.stride(0), _ptr(Ginv), f, _ptr(W), W.stride(0), _stream()),
+               "wmf_dense_right_multiply")
+    X = torch.empty((csr.shape[0], f), dtype=torch.float32, device=Y.device)
+    _lib.check(lib.wmf_spmm(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), csr.shape[0], _ptr(W), W.stride(0), f,
+                            _ptr(X), X.stride(0), _stream()), "wmf_spmm")
+    return X

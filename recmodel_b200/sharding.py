@@ -1,0 +1,68 @@
+"""Row partitioning and factor exchange for multi-GPU ALS.
+
+Within a half-step every row's solve is independent given the full fixed-side factors
+(wmf_model.py:220-239), so rank g owns a contiguous row range of the count matrix (user
+half-step) and of its transpose (item half-step); the only exchange is an all-gather of the
+new factor shard after each half-step (NCCL over NVLink/NVSwitch on GPUs, gloo on CPU in the
+tests). Row -> rank assignment never changes a row's arithmetic, so N-GPU factors equal
+1-GPU factors bit for bit.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def dist_info(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def row_costs(counts, f):
+    """Per-row work model: n_r * f^2 (Gram) + f^3/3 (solve) (SURVEY.md §8d flop terms)."""
+    counts = np.asarray(counts, dtype=np.float64)
+    return counts * float(f) * f + np.where(counts > 0, float(f) ** 3 / 3.0, 1.0)
+
+
+def balanced_row_partition(counts, world, f):
+    """Contiguous row ranges [b[g], b[g+1]) with near-equal summed cost. Returns int64 array of
+    world+1 boundaries (monotone, b[0]=0, b[-1]=rows)."""
+    counts = np.asarray(counts)
+    rows = len(counts)
+    if world <= 1 or rows == 0:
+        return np.array([0] + [rows] * max(world, 1), dtype=np.int64)
+    csum = np.cumsum(row_costs(counts, f))
+    targets = csum[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(csum, targets, side="left") + 1
+    bounds = np.concatenate([[0], np.minimum(cuts, rows), [rows]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+def all_gather_rows(local, bounds, group=None):
+    """Concatenate row shards [bounds[g], bounds[g+1]) from every rank into the full matrix.
+    Shards have different heights, so each rank pads to the tallest shard; one all-gather."""
+    rank, world = dist_info(group)
+    if world == 1:
+        return local
+    heights = np.diff(bounds)
+    hmax = int(heights.max())
+    f = local.shape[1]
+    send = local
+    if local.shape[0] != hmax:
+        send = torch.zeros((hmax, f), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
+    recv = torch.empty((world * hmax, f), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    if int(heights.min()) == hmax:
+        return recv
+    full = torch.empty((int(bounds[-1]), f), dtype=local.dtype, device=local.device)
+    for g in range(world):
+        full[int(bounds[g]):int(bounds[g + 1])] = recv[g * hmax: g * hmax + int(heights[g])]
+    return full
+
+
+def all_reduce_sum_(t, group=None):
+    _, world = dist_info(group)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t

@@ -28,6 +28,27 @@ def _popularity(n_items, exponent, rng):
     return w / w.sum()
 
 
+def make_counts_cached(n_users, n_items, nnz, seed=DEFAULT_SEED, planted_rank=0, cache_dir=None):
+    """``make_counts`` with an on-disk cache (generation of 20 M entries takes ~40 s of host
+    time; tests and the bench in one session share it)."""
+    import os
+    cache_dir = cache_dir or os.environ.get("WMF_SYNTH_CACHE", "/tmp/wmf_synth_cache")
+    path = os.path.join(cache_dir, f"counts_{n_users}_{n_items}_{nnz}_{seed}_{planted_rank}.npz")
+    if os.path.exists(path):
+        try:
+            return scipy.sparse.load_npz(path)
+        except Exception:
+            pass
+    mat = make_counts(n_users, n_items, nnz, seed=seed, planted_rank=planted_rank)
+    try:
+        os.makedirs(cache_dir, exist_ok=True)
+        scipy.sparse.save_npz(path + ".tmp.npz", mat, compressed=False)
+        os.replace(path + ".tmp.npz", path)
+    except OSError:
+        pass
+    return mat
+
+
 def make_counts(n_users, n_items, nnz, seed=DEFAULT_SEED, planted_rank=0, exponent=0.8,
                 sigma=1.0, max_row_frac=0.5):
     """CSR float32 count matrix with exactly ``nnz`` distinct entries (or slightly fewer if

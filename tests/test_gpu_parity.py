@@ -1,0 +1,406 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded
+inputs and against the committed golden vectors of the executed reference.
+
+Bars (BASELINE.json north_star): factors within 1e-4 relative per half-step (row-wise L2),
+predict bit-exact, top-N index sets identical, Recall within 0.005 absolute.
+"""
+import numpy as np
+import pytest
+import scipy.sparse
+import torch
+
+from conftest import WEIGHTED_CASES, csr_from, load_golden, row_rel_err
+from oracle import wmf_oracle as orc
+from recmodel_b200 import WMF, _lib, engine
+from recmodel_b200.engine import DeviceCSR
+from recmodel_b200.synthetic import make_counts, make_counts_cached, split_train_test
+
+pytestmark = pytest.mark.gpu
+
+HALF_STEP_TOL = 1e-4
+ALGOS = [("simt", _lib.ALGO_SIMT), ("tcgen05", _lib.ALGO_TCGEN05)]
+
+
+def dev(a, cuda_device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+
+
+def tc_supported(f, bias):
+    return bool(_lib.load().wmf_als_half_step_supports(_lib.ALGO_TCGEN05, int(f), int(bool(bias))))
+
+
+def half_step_tol(Y, C, ref32, bias):
+    """1e-4, widened only where the reference's own fp32 arithmetic is noisier than that
+    against the fp64 restatement (tiny rank-deficient fixtures)."""
+    step = orc.half_step_bias if bias else orc.half_step
+    x64 = step(Y, C, 0.1, np.float64)
+    noise = row_rel_err(ref32, x64)
+    return x64, max(HALF_STEP_TOL, 2.0 * noise)
+
+
+def run_half_step(Y, C, bias, algo, cuda_device, use_row_order=True):
+    Yd = dev(Y, cuda_device)
+    Cd = DeviceCSR.from_scipy(C, cuda_device)
+    G = engine.gram(Yd, 0.1, ones_col0=bias)
+    X = engine.half_step(Cd, Yd, G, bias=bias, algo=algo, use_row_order=use_row_order)
+    torch.cuda.synchronize()
+    return X.cpu().numpy(), G.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------- K6, K1
+def test_device_is_b200(cuda_device):
+    assert _lib.require_device() >= 100
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_preprocess_matches_numpy(cuda_device):
+    x = np.random.default_rng(0).integers(1, 50, size=100_003).astype(np.float32)
+    for mode in ("log", "linear"):
+        d = engine.preprocess_(dev(x, cuda_device).clone(), mode, 10, 1).cpu().numpy()
+        np.testing.assert_allclose(d, orc.preprocess_counts(x, mode, 10, 1), rtol=3e-7)
+    with pytest.raises(ValueError):
+        engine.preprocess_(dev(x, cuda_device), "sqrt", 10, 1)
+
+
+@pytest.mark.parametrize("n,f,ones", [(1, 8, False), (1000, 16, False), (3706, 65, True), (26_744, 128, False),
+                                      (5000, 129, True), (777, 256, False), (300, 257, True)])
+def test_gram_matches_fp64(cuda_device, n, f, ones):
+    Y = np.random.default_rng(n + f).random((n, f)).astype(np.float32)
+    G = engine.gram(dev(Y, cuda_device), 0.1, ones_col0=ones).cpu().numpy()
+    Y64 = Y.astype(np.float64)
+    if ones:
+        Y64[:, 0] = 1
+    ref = Y64.T @ Y64 + 0.1 * np.eye(f)
+    assert np.max(np.abs(G - ref) / np.abs(ref).max()) < 2e-6
+    G2 = engine.gram(dev(Y, cuda_device), 0.1, ones_col0=ones).cpu().numpy()
+    np.testing.assert_array_equal(G, G2)  # deterministic reduction order
+
+
+def test_transpose_matches_scipy(cuda_device):
+    C = make_counts(700, 450, 20_000, seed=21)
+    CT = DeviceCSR.from_scipy(C, cuda_device).transpose().to_scipy()
+    ref = C.T.tocsr()
+    np.testing.assert_array_equal(CT.indptr, ref.indptr)
+    np.testing.assert_array_equal(CT.indices, ref.indices)
+    np.testing.assert_array_equal(CT.data, ref.data)
+
+
+# ------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("algo_name,algo", ALGOS)
+@pytest.mark.parametrize("name,dim,bias,mode", WEIGHTED_CASES)
+def test_half_step_vs_reference_golden(cuda_device, name, dim, bias, mode, algo_name, algo):
+    f = dim + 1 if bias else dim
+    if algo == _lib.ALGO_TCGEN05 and not tc_supported(f, bias):
+        pytest.skip("shape not taken by the tcgen05 path")
+    g = load_golden(name)
+    C = csr_from(g, "train")
+    C.data = orc.preprocess_counts(C.data, mode, 10, 1)
+    CT = C.T.tocsr()
+    x64, tol = half_step_tol(g["items0"], C, g["users_half1"], bias)
+    X, _ = run_half_step(g["items0"], C, bias, algo, cuda_device)
+    assert row_rel_err(X, g["users_half1"]) < tol
+    assert row_rel_err(X, x64) < tol
+    x64, tol = half_step_tol(g["users_half1"], CT, g["items_half1"], bias)
+    Xi, _ = run_half_step(g["users_half1"], CT, bias, algo, cuda_device)
+    assert row_rel_err(Xi, g["items_half1"]) < tol
+
+
+@pytest.mark.parametrize("algo_name,algo", ALGOS)
+@pytest.mark.parametrize("users,items,nnz,dim,bias", [
+    (6040, 3706, 1_000_000, 64, True),     # config 1 in full (ML-1M shape, bias)
+    (6040, 3706, 1_000_000, 64, False),
+    (3000, 2000, 300_000, 128, False),     # config-2 arithmetic (f=128) at an oracle-sized shape
+    (1500, 1200, 150_000, 128, True),
+])
+def test_half_step_vs_oracle_realistic(cuda_device, users, items, nnz, dim, bias, algo_name, algo):
+    f = dim + 1 if bias else dim
+    if algo == _lib.ALGO_TCGEN05 and not tc_supported(f, bias):
+        pytest.skip("shape not taken by the tcgen05 path")
+    C = make_counts_cached(users, items, nnz, seed=31)
+    C.data = orc.preprocess_counts(C.data)
+    CT = C.T.tocsr()
+    Y = orc.init_items(items, dim, bias)
+    step = orc.half_step_bias if bias else orc.half_step
+    ref_u = step(Y, C, 0.1)
+    X, _ = run_half_step(Y, C, bias, algo, cuda_device)
+    assert row_rel_err(X, ref_u) < HALF_STEP_TOL
+    # second half-step from the reference's users (mixed-sign factors, the steady-state regime)
+    sel = slice(0, min(items, 800))
+    ref_i = step(ref_u, CT[sel], 0.1)
+    Xi, _ = run_half_step(ref_u, CT[sel], bias, algo, cuda_device)
+    assert row_rel_err(Xi, ref_i) < HALF_STEP_TOL
+
+
+@pytest.mark.parametrize("algo_name,algo", ALGOS)
+@pytest.mark.parametrize("f,bias", [(8, False), (9, True), (64, False), (65, True), (128, False), (129, True),
+                                    (200, False), (256, False), (257, True)])
+def test_half_step_edge_rows(cuda_device, f, bias, algo_name, algo):
+    """Empty rows, 1-entry rows, a row much longer than f, unsorted column order, explicit zero
+    weights (SURVEY.md §4 unit level)."""
+    if algo == _lib.ALGO_TCGEN05 and not tc_supported(f, bias):
+        pytest.skip("shape not taken by the tcgen05 path")
+    rng = np.random.default_rng(f)
+    N = 900
+    lens = [0, 1, 1, 0, 2, 5, 33, 700, 0, 17, 64, 3, 0]
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    indices = np.concatenate([rng.permutation(N)[:n] for n in lens]).astype(np.int32)  # unsorted inside rows
+    data = (rng.random(indptr[-1]) * 20).astype(np.float32)
+    data[::7] = 0.0
+    C = scipy.sparse.csr_matrix((data, indices, indptr), shape=(len(lens), N))
+    Y = (rng.standard_normal((N, f)) * 0.3).astype(np.float32)
+    if bias:
+        Y[:, 0] = rng.random(N).astype(np.float32)
+    step = orc.half_step_bias if bias else orc.half_step
+    ref = step(Y, C, 0.1)
+    x64, tol = half_step_tol(Y, C, ref, bias)
+    X, _ = run_half_step(Y, C, bias, algo, cuda_device)
+    assert np.all(X[np.array(lens) == 0] == 0)
+    assert row_rel_err(X, x64) < tol
+    X2, _ = run_half_step(Y, C, bias, algo, cuda_device, use_row_order=False)
+    np.testing.assert_array_equal(X, X2)  # processing order never changes a row's arithmetic
+
+
+@pytest.mark.parametrize("algo_name,algo", ALGOS)
+def test_half_step_indefinite_falls_back_to_lu(cuda_device, algo_name, algo):
+    """Negative confidence weights make A indefinite; the reference's sgesv still solves it."""
+    rng = np.random.default_rng(5)
+    N, f = 400, 64
+    C = scipy.sparse.random(40, N, density=0.2, format="csr", dtype=np.float32, random_state=3)
+    C.data = (-(C.data * 30) - 5).astype(np.float32)
+    Y = (rng.standard_normal((N, f)) * 0.4).astype(np.float32)
+    ref = orc.half_step(Y, C, 0.1)
+    x64, tol = half_step_tol(Y, C, ref, False)
+    X, _ = run_half_step(Y, C, False, algo, cuda_device)
+    assert np.all(np.isfinite(X))
+    assert row_rel_err(X, x64) < max(tol, 1e-3)  # indefinite systems: conditioning-limited
+
+
+def test_half_step_full_size_properties(cuda_device):
+    """Config 2 at full size (138 493 x 26 744, 20 M entries, f=128): size-independent checks.
+    (1) normal-equation residual of sampled rows in fp64; (2) bitwise determinism;
+    (3) a 2-way row shard reproduces the unsharded rows bit for bit."""
+    users, items, nnz, f = 138_493, 26_744, 20_000_000, 128
+    C = make_counts_cached(users, items, nnz)
+    C.data = orc.preprocess_counts(C.data)
+    Y = orc.init_items(items, f, False)
+    Yd = dev(Y, cuda_device)
+    Cd = DeviceCSR.from_scipy(C, cuda_device)
+    G = engine.gram(Yd, 0.1)
+    X = engine.half_step(Cd, Yd, G).cpu().numpy()
+    assert np.all(np.isfinite(X))
+    G64 = Y.astype(np.float64).T @ Y.astype(np.float64) + 0.1 * np.eye(f)
+    rows = np.concatenate([np.random.default_rng(1).integers(0, users, 48), [int(np.argmax(np.diff(C.indptr)))]])
+    for r in rows:
+        lo, hi = C.indptr[r], C.indptr[r + 1]
+        if lo == hi:
+            assert np.all(X[r] == 0)
+            continue
+        Yr = Y[C.indices[lo:hi]].astype(np.float64)
+        d = C.data[lo:hi].astype(np.float64)
+        A = G64 + (Yr * d[:, None]).T @ Yr
+        x = np.linalg.solve(A, (d + 1) @ Yr)
+        assert np.linalg.norm(X[r] - x) / np.linalg.norm(x) < HALF_STEP_TOL
+    X2 = engine.half_step(Cd, Yd, G).cpu().numpy()
+    np.testing.assert_array_equal(X, X2)
+    half = users // 2
+    Xa = engine.half_step(Cd.row_slice(0, half), Yd, G).cpu().numpy()
+    np.testing.assert_array_equal(Xa, X[:half])
+
+
+# ------------------------------------------------------------------------------- R8, K3
+@pytest.mark.parametrize("f,bias", [(5, False), (7, True), (16, False), (64, False), (65, True), (128, False),
+                                    (129, True), (200, False), (256, False), (257, True), (300, False)])
+def test_predict_bit_exact(cuda_device, f, bias):
+    rng = np.random.default_rng(f)
+    U = (rng.standard_normal((300, f)) * 10 ** rng.uniform(-2, 2, (300, f))).astype(np.float32)
+    V = (rng.standard_normal((500, f)) * 10 ** rng.uniform(-2, 2, (500, f))).astype(np.float32)
+    us, it = rng.integers(0, 300, 4001), rng.integers(0, 500, 4001)
+    m = WMF(num_items=500, num_users=300, dim=f - 1 if bias else f, gamma=0.1, weighted=True, bias=bias)
+    m.users, m.items = U, V
+    np.testing.assert_array_equal(m.predict(us, it), orc.predict(U, V, us, it, bias))
+    np.testing.assert_array_equal(m.predict(7, np.arange(500)), orc.predict(U, V, 7, np.arange(500), bias))
+    with pytest.raises(ValueError):
+        m.predict([1, 2, 3], [1, 2])
+
+
+@pytest.mark.parametrize("name,dim,bias,mode", WEIGHTED_CASES)
+def test_predict_and_metrics_vs_golden(cuda_device, name, dim, bias, mode):
+    g = load_golden(name)
+    te = csr_from(g, "test")
+    m = WMF(num_items=g["items_final"].shape[0], num_users=g["users_final"].shape[0], dim=dim, gamma=0.1,
+            weighted=True, bias=bias)
+    m.users, m.items = g["users_final"], g["items_final"]
+    np.testing.assert_array_equal(m.predict(g["pred_users"], g["pred_items"]), g["pred"])
+    assert float(m.eval_prec(te)) == pytest.approx(float(g["mse_final"]), rel=2e-6)
+    assert float(m.eval_prec(te, "rmse")) == pytest.approx(float(g["rmse_final"]), rel=2e-6)
+    assert float(m.eval_prec(te, metric="MAE")) == pytest.approx(float(g["mae_final"]), rel=2e-6)
+    with pytest.raises(ValueError):
+        m.eval_prec(te, "nope")
+    te0 = te.copy()
+    te0.data[::3] = 0.0  # explicit zeros are skipped like nonzero() does
+    ref = orc.eval_prec_f64(g["users_final"], g["items_final"], te0, bias)
+    assert float(m.eval_prec(te0)) == pytest.approx(ref, rel=2e-6)
+
+
+def test_sddmm_loss_large_and_deterministic(cuda_device):
+    C = make_counts_cached(6040, 3706, 1_000_000, seed=31)
+    rng = np.random.default_rng(2)
+    U = (rng.standard_normal((6040, 128)) * 0.2).astype(np.float32)
+    V = (rng.standard_normal((3706, 128)) * 0.2).astype(np.float32)
+    Cd = DeviceCSR.from_scipy(C, cuda_device)
+    s1 = engine.sddmm_loss(Cd, dev(U, cuda_device), dev(V, cuda_device)).cpu().numpy()
+    s2 = engine.sddmm_loss(Cd, dev(U, cuda_device), dev(V, cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(s1, s2)
+    assert s1[2] == C.nnz
+    assert s1[0] / s1[2] == pytest.approx(orc.eval_prec_f64(U, V, C, False), rel=1e-9)
+
+
+# ------------------------------------------------------------------------------- R10
+@pytest.mark.parametrize("name,dim,bias,mode", WEIGHTED_CASES)
+def test_rank_vs_golden(cuda_device, name, dim, bias, mode):
+    g = load_golden(name)
+    V = g["items_final"]
+    m = WMF(num_items=V.shape[0], num_users=g["users_final"].shape[0], dim=dim, gamma=0.1, weighted=True, bias=bias)
+    m.users, m.items = g["users_final"], V
+    all_items = np.arange(V.shape[0])
+    for k, u in enumerate(g["rank_users"]):
+        top = m.rank(all_items, int(u), 10)
+        assert top.dtype == all_items.dtype and len(top) == 10
+        assert set(top.tolist()) == set(g["rank_top10"][k].tolist())
+        s = g["rank_scores"][k]
+        np.testing.assert_array_equal(s[top], s[g["rank_top10"][k]])  # same order up to exact ties
+    lst = m.rank(all_items, [int(u) for u in g["rank_users"]], 10)
+    assert isinstance(lst, list) and len(lst) == len(g["rank_users"])
+    for k in range(len(lst)):
+        np.testing.assert_array_equal(lst[k], m.rank(all_items, int(g["rank_users"][k]), 10))
+    near = max(V.shape[0] - 3, 1)
+    for k, u in enumerate(g["rank_users"][:4]):
+        s = g["rank_scores"][k]
+        top = m.rank(all_items, int(u), near)
+        np.testing.assert_array_equal(s[top], s[g["rank_near_full"][k]])
+    assert len(m.rank(all_items, 3)) == V.shape[0]           # topn=None ranks everything
+    assert len(m.rank(all_items[:5], 3, 50)) == 5            # topn > len(items) returns len(items)
+    sub = np.array([9, 3, 3, 17, 4], dtype=np.int32)         # duplicates + caller's dtype
+    out = m.rank(sub, 2, 3)
+    assert out.dtype == np.int32 and set(out.tolist()) <= set(sub.tolist())
+
+
+@pytest.mark.parametrize("f,bias,ni,topn", [(64, False, 3706, 100), (128, False, 26_744, 100), (65, True, 5000, 20),
+                                            (257, True, 1500, 1024), (16, False, 40, 40), (128, False, 3000, 2000)])
+def test_rank_sets_bit_exact_vs_oracle(cuda_device, f, bias, ni, topn):
+    rng = np.random.default_rng(ni + f)
+    nu = 37
+    U = (rng.standard_normal((nu, f)) * 0.5).astype(np.float32)
+    V = (rng.standard_normal((ni, f)) * 0.5).astype(np.float32)
+    V[ni // 2] = V[ni // 3]  # an exact tie
+    m = WMF(num_items=ni, num_users=nu, dim=f - 1 if bias else f, gamma=0.1, weighted=True, bias=bias)
+    m.users, m.items = U, V
+    cand = np.arange(ni)
+    got = m.rank_batch(cand, np.arange(nu), topn)
+    for u in range(nu):
+        s = orc.rank_scores(U, V, cand, u, bias)
+        kth = np.sort(s)[-topn]
+        must = set(np.nonzero(s > kth)[0].tolist())
+        may = set(np.nonzero(s >= kth)[0].tolist())
+        sel = set(got[u].tolist())
+        assert len(sel) == topn and must <= sel <= may
+        assert np.all(np.diff(s[got[u]]) <= 0)  # descending
+
+
+def test_rank_all_equal_scores_ties_by_position(cuda_device):
+    m = WMF(num_items=300, num_users=2, dim=8, gamma=0.1, weighted=True)
+    m.users, m.items = np.ones((2, 8), np.float32), np.ones((300, 8), np.float32)
+    np.testing.assert_array_equal(m.rank(np.arange(300), 0, 7), np.arange(7))
+
+
+# ------------------------------------------------------------------------------- R2, R11, R12
+@pytest.mark.parametrize("algo_name", ["simt", "tcgen05"])
+@pytest.mark.parametrize("name,dim,bias,mode", WEIGHTED_CASES)
+def test_train_vs_reference_golden(cuda_device, name, dim, bias, mode, algo_name, capsys):
+    f = dim + 1 if bias else dim
+    if algo_name == "tcgen05" and not tc_supported(f, bias):
+        pytest.skip("shape not taken by the tcgen05 path")
+    g = load_golden(name)
+    tr, te = csr_from(g, "train"), csr_from(g, "test")
+    tr_before = tr.copy()
+    m = WMF(num_items=tr.shape[1], num_users=tr.shape[0], dim=dim, gamma=0.1, weighted=True, bias=bias, seed=1993,
+            algo=algo_name)
+    it = m.train(tr.copy(), iterations=int(g["train_iter"]) + 1, eval_mat=te, count_mat=tr, cores=1,
+                 stopping_rounds=99, pre_process_count=mode)
+    assert it == int(g["train_iter"])
+    assert (tr != tr_before).nnz == 0  # inputs are never mutated
+    # several half-steps compound; the per-half-step bar is checked above
+    ill = name in ("weighted_bias_f64", "weighted_nobias_f128", "weighted_nobias_f64_linear")
+    tol = 2e-2 if ill else 2e-3
+    assert row_rel_err(m.users, g["users_final"]) < tol
+    assert row_rel_err(m.items, g["items_final"]) < tol
+    assert float(m.eval_prec(te)) == pytest.approx(float(g["mse_final"]), rel=1e-3)
+    if not ill:
+        m2 = WMF(num_items=tr.shape[1], num_users=tr.shape[0], dim=dim, gamma=0.1, weighted=True, bias=bias,
+                 algo=algo_name)
+        assert m2.train(tr, iterations=12, eval_mat=te, count_mat=tr, cores=4, stopping_rounds=2,
+                        pre_process_count=mode) == int(g["early_iter"])
+        rec = m.eval_topn(te.copy(), topn=g["topn"], rand_sampled=100, cores=1, random_state=7)
+        got = np.array([rec[f"Recall@{k}"] for k in g["topn"]], dtype=np.float64)
+        assert np.max(np.abs(got - g["recall"])) <= 0.005
+
+
+def test_train_argument_errors(cuda_device):
+    g = load_golden("weighted_nobias_f16")
+    tr, te = csr_from(g, "train"), csr_from(g, "test")
+    m = WMF(num_items=tr.shape[1], num_users=tr.shape[0], dim=16, gamma=0.1, weighted=True)
+    with pytest.raises(ValueError):
+        m.train(tr, 1, eval_mat=te, count_mat=tr, pre_process_count="sqrt")
+    with pytest.raises(ValueError):
+        m.train(tr, 1, eval_mat=te, count_mat=tr, cores=0)
+    with pytest.raises(AttributeError):
+        m.train(tr, 1, eval_mat=None, count_mat=tr, cores=1)
+    mb = WMF(num_items=tr.shape[1], num_users=tr.shape[0], dim=16, gamma=0.1, weighted=False, bias=True)
+    with pytest.raises(ValueError):
+        mb.train(tr, 1, eval_mat=te)
+
+
+def test_recompute_factors_methods(cuda_device):
+    g = load_golden("weighted_bias_f8")
+    C = csr_from(g, "train")
+    C.data = orc.preprocess_counts(C.data)
+    m = WMF(num_items=C.shape[1], num_users=C.shape[0], dim=8, gamma=0.1, weighted=True, bias=True)
+    Y = g["items0"].copy()
+    X = m.recompute_factors_bias(Y, C, 0.1, cores=1)
+    _, tol = half_step_tol(g["items0"], C, g["users_half1"], True)
+    assert row_rel_err(X, g["users_half1"]) < tol
+    assert np.all(Y[:, 0] == 1)  # the reference overwrites the caller's bias column (wmf_model.py:331)
+    g2 = load_golden("weighted_nobias_f16")
+    C2 = csr_from(g2, "train")
+    C2.data = orc.preprocess_counts(C2.data)
+    m2 = WMF(num_items=C2.shape[1], num_users=C2.shape[0], dim=16, gamma=0.1, weighted=True)
+    assert row_rel_err(m2.recompute_factors(g2["items0"], C2, 0.1), g2["users_half1"]) < HALF_STEP_TOL
+    assert row_rel_err(m2.recompute_factors_par(g2["items0"], C2, 0.1, cores=4), g2["users_half1"]) < HALF_STEP_TOL
+
+
+def test_unweighted_vs_golden(cuda_device):
+    g = load_golden("unweighted_f12")
+    tr, te = csr_from(g, "train"), csr_from(g, "test")
+    m = WMF(num_items=tr.shape[1], num_users=tr.shape[0], dim=12, gamma=0.1)  # weighted=None -> unweighted
+    assert m.train(tr, 1, eval_mat=te, cores=1, stopping_rounds=99) == 0
+    assert row_rel_err(m.users, g["users_ep1"]) < 5e-4
+    assert row_rel_err(m.items, g["items_ep1"]) < 5e-4
+    m = WMF(num_items=tr.shape[1], num_users=tr.shape[0], dim=12, gamma=0.1)
+    assert m.train(tr, 3, eval_mat=te, cores=1, stopping_rounds=99) == int(g["train_iter"])
+    assert float(m.eval_prec(te)) == pytest.approx(float(g["mse_final"]), rel=2e-3)
+
+
+def test_recall_quality_planted_structure(cuda_device):
+    """End-to-end quality: Recall@20 on a planted low-rank matrix vs the oracle trained the same
+    way (north_star: within 0.005 absolute)."""
+    full = make_counts(1200, 800, 60_000, seed=41, planted_rank=8)
+    tr, te = split_train_test(full)
+    m = WMF(num_items=800, num_users=1200, dim=16, gamma=0.1, weighted=True)
+    m.train(tr, 4, eval_mat=te, count_mat=tr, cores=1, stopping_rounds=99)
+    U, V, _, _ = orc.train(orc.init_items(800, 16, False), tr, 4, te, count_mat=tr, gamma=0.1, stopping_rounds=99)
+    topn = np.array([20])
+    ours = m.eval_topn(te.copy(), topn=topn, rand_sampled=200, cores=1, random_state=3)["Recall@20"]
+    ref = orc.eval_topn(lambda it, u, k: orc.rank(U, V, it, u, k), 800, te, topn, rand_sampled=200,
+                        random_state=3)["Recall@20"]
+    assert ref > 0.3
+    assert abs(float(ours) - float(ref)) <= 0.005

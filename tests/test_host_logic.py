@@ -1,0 +1,97 @@
+"""Host-side logic: constructor parity with the reference, row partitioning, the gloo
+world_size=2 exchange, the synthetic generator and the split. CPU only."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+from conftest import ROOT, load_golden
+from recmodel_b200 import WMF, WMFModel, sharding, train_test_split_sparse_mat
+from recmodel_b200.synthetic import make_counts
+
+
+def test_constructor_matches_reference_init():
+    g = load_golden("weighted_bias_f8")
+    m = WMF(num_items=g["items0"].shape[0], num_users=int(g["train_shape"][0]), dim=8, gamma=0.1, weighted=True,
+            bias=True, seed=1993)
+    np.testing.assert_array_equal(m.items, g["items0"])
+    assert m.users is None and m.dim == 8 and m.gamma == 0.1 and m.weighted is True and m.dtype == "float32"
+    assert WMFModel is WMF
+    with pytest.raises(ValueError):
+        WMF(5, 4, 3, 0.1, dtype="float64")
+
+
+def test_synthetic_generator_is_deterministic_and_canonical():
+    a = make_counts(300, 200, 5000, seed=3)
+    b = make_counts(300, 200, 5000, seed=3)
+    assert a.nnz == 5000 and (a != b).nnz == 0
+    assert a.has_sorted_indices
+    for r in range(a.shape[0]):
+        idx = a.indices[a.indptr[r]:a.indptr[r + 1]]
+        assert np.all(np.diff(idx) > 0)
+    assert a.data.dtype == np.float32 and a.data.min() >= 1 and a.data.max() <= 5
+
+
+def test_split_keeps_reference_rng_semantics():
+    m = make_counts(200, 150, 4000, seed=4)
+    tr, te = train_test_split_sparse_mat(m, train=0.8, seed=1993)
+    assert tr.nnz + te.nnz == m.nnz and (tr.multiply(te)).nnz == 0
+    np.random.seed(1993)
+    mask = np.random.rand(m.nnz) < 0.8
+    assert tr.nnz == int(mask.sum())
+    assert m.nnz == 4000  # the input is not zeroed
+
+
+def test_balanced_row_partition_properties():
+    rng = np.random.default_rng(0)
+    counts = (rng.pareto(1.2, size=5000) * 20).astype(np.int64)
+    for world in (1, 2, 4, 8):
+        b = sharding.balanced_row_partition(counts, world, 128)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == len(counts) and np.all(np.diff(b) >= 0)
+        cost = sharding.row_costs(counts, 128)
+        per = np.array([cost[b[g]:b[g + 1]].sum() for g in range(world)])
+        assert per.max() <= cost.sum() / world + cost.max() + 1e-6
+    assert list(sharding.balanced_row_partition(np.zeros(0), 4, 16)) == [0, 0, 0, 0, 0]
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from recmodel_b200 import sharding
+from oracle import wmf_oracle as orc
+from recmodel_b200.synthetic import make_counts
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, world = sharding.dist_info()
+C = make_counts(90, 60, 1500, seed=9); C.data = orc.preprocess_counts(C.data)
+CT = C.T.tocsr()
+Y = orc.init_items(60, 8, False)
+ub = sharding.balanced_row_partition(np.diff(C.indptr), world, 8)
+ib = sharding.balanced_row_partition(np.diff(CT.indptr), world, 8)
+# each rank solves only its rows (the oracle stands in for the kernel on CPU), then all-gather
+Xl = orc.half_step(Y, C[ub[rank]:ub[rank+1]], 0.1)
+users = sharding.all_gather_rows(torch.from_numpy(Xl), ub).numpy()
+Il = orc.half_step(users, CT[ib[rank]:ib[rank+1]], 0.1)
+items = sharding.all_gather_rows(torch.from_numpy(Il), ib).numpy()
+ref_u = orc.half_step(Y, C, 0.1); ref_i = orc.half_step(ref_u, CT, 0.1)
+assert np.array_equal(users, ref_u) and np.array_equal(items, ref_i), "sharded != single"
+s = torch.tensor([1.0 + rank, 2.0, 3.0], dtype=torch.float64)
+sharding.all_reduce_sum_(s)
+assert s.tolist() == [3.0, 4.0, 6.0]
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_sharded_epoch_equals_single(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o
