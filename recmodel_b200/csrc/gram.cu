@@ -4,7 +4,11 @@
 // half-step's, and the read of Y (n*f*4 B) is the algorithmic traffic, so this kernel is
 // HBM-bound by design: each CTA streams a contiguous chunk of rows once through shared
 // memory and keeps a 64x64 output block per (bi,bj) in registers (4x4 per thread).
-// Partials go to workspace and are reduced in a fixed order -> bit-reproducible.
+// Accuracy: with all-positive factors (the U[0,1) initialisation) G is a huge rank-one term
+// plus a small well-conditioned part, and the half-step solution is ~1e2..1e3 times more
+// sensitive to relative errors in G than to anything else. So FP32 FMAs only run over one
+// staged tile of 32 rows; tiles are summed in double, partials are stored and reduced in
+// double in a fixed order (bit-reproducible), and G is rounded to fp32 once.
 #include "common.cuh"
 
 namespace wmf {
@@ -15,18 +19,18 @@ constexpr int G_THREADS = 256;
 
 __global__ __launch_bounds__(G_THREADS) void gram_partial_kernel(const float* __restrict__ Y, int64_t n, int f,
                                                                  int64_t ldy, int ones_col0, int rows_per_cta,
-                                                                 float* __restrict__ partial) {
+                                                                 double* __restrict__ partial) {
     __shared__ float sa[GR][GB + 4];
     __shared__ float sb[GR][GB + 4];
     const int nblk = (f + GB - 1) / GB;
     const int bi = blockIdx.y / nblk, bj = blockIdx.y % nblk;
     const int tid = threadIdx.x;
     const int ty = tid / 16, tx = tid % 16;
-    float acc[4][4];
+    double dacc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int b = 0; b < 4; ++b) dacc[a][b] = 0.0;
 
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
     int64_t r1 = r0 + rows_per_cta;
@@ -46,6 +50,11 @@ __global__ __launch_bounds__(G_THREADS) void gram_partial_kernel(const float* __
             sb[rr][c] = vb;
         }
         __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 #pragma unroll 8
         for (int rr = 0; rr < GR; ++rr) {
             float4 a4 = *reinterpret_cast<const float4*>(&sa[rr][ty * 4]);
@@ -57,26 +66,32 @@ __global__ __launch_bounds__(G_THREADS) void gram_partial_kernel(const float* __
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
         }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dacc[a][b] += (double)acc[a][b];
         __syncthreads();
     }
-    float* out = partial + (size_t)blockIdx.x * f * f;
+    double* out = partial + (size_t)blockIdx.x * f * f;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             int i = bi * GB + ty * 4 + a, j = bj * GB + tx * 4 + b;
-            if (i < f && j < f) out[(size_t)i * f + j] = acc[a][b];
+            if (i < f && j < f) out[(size_t)i * f + j] = dacc[a][b];
         }
 }
 
-__global__ void gram_reduce_kernel(const float* __restrict__ partial, int nparts, int f, float lambda,
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, int f, float lambda,
                                    float* __restrict__ G) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= f * f) return;
-    float s = 0.f;
+    double s = 0.0;
     for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * f * f + e];
-    if (e / f == e % f) s += lambda;
-    G[e] = s;
+    // np.dot(Y.T, Y) is rounded to fp32 before lambda*eye is added (wmf_model.py:215)
+    float g = (float)s;
+    if (e / f == e % f) g = __fadd_rn(g, lambda);
+    G[e] = g;
 }
 
 static int gram_parts(int64_t n) {
@@ -95,7 +110,7 @@ extern "C" {
 
 size_t wmf_gram_workspace_bytes(int64_t n, int f) {
     if (n < 0 || f <= 0) return 0;
-    return (size_t)gram_parts(n) * f * f * sizeof(float);
+    return (size_t)gram_parts(n) * f * f * sizeof(double);
 }
 
 int wmf_gram(const float* Y, int64_t n, int f, int64_t ldy, float lambda, int ones_col0, float* G, void* ws,
@@ -114,9 +129,9 @@ int wmf_gram(const float* Y, int64_t n, int f, int64_t ldy, float lambda, int on
     if (rows_per_cta == 0) rows_per_cta = GR;
     int nblk = (f + GB - 1) / GB;
     dim3 grid(parts, nblk * nblk);
-    gram_partial_kernel<<<grid, G_THREADS, 0, st>>>(Y, n, f, ldy, ones_col0, rows_per_cta, (float*)ws);
+    gram_partial_kernel<<<grid, G_THREADS, 0, st>>>(Y, n, f, ldy, ones_col0, rows_per_cta, (double*)ws);
     WMF_LAUNCH_CHECK("gram_partial_kernel");
-    gram_reduce_kernel<<<(f * f + 255) / 256, 256, 0, st>>>((const float*)ws, parts, f, lambda, G);
+    gram_reduce_kernel<<<(f * f + 255) / 256, 256, 0, st>>>((const double*)ws, parts, f, lambda, G);
     WMF_LAUNCH_CHECK("gram_reduce_kernel");
     return WMF_OK;
 }

@@ -55,8 +55,13 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
         }
         bool use_lu = p.bias != 0;
         while (true) {
-            for (int e = tid; e < f * f; e += HS_THREADS) A[(e / f) * lda + (e % f)] = p.G[e];
-            float bacc0 = 0.f, bacc1 = 0.f;
+            // The weighted Gram is summed from zero and G is added ONCE at the end, as the reference
+            // does (wmf_model.py:237-239): adding small chunks into the large entries of G would round
+            // every partial sum at G's magnitude.
+            for (int e = tid; e < f * f; e += HS_THREADS) A[(e / f) * lda + (e % f)] = 0.0f;
+            // rhs: fp32 FMAs inside one staged chunk, chunks summed in double (a plain sequential
+            // fp32 sum over a 2000-entry row is 3x noisier than the reference's sgemv)
+            double bacc0 = 0.0, bacc1 = 0.0;
             __syncthreads();
             for (int64_t base = lo; base < hi; base += KC) {
                 const int kc = (int)((hi - base) < KC ? (hi - base) : KC);
@@ -78,10 +83,14 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
                 }
                 __syncthreads();
                 if (tid < f) {
-                    for (int k = 0; k < KC; ++k) bacc0 = fmaf(ds[k], Ys[k * FP + tid], bacc0);
+                    float part = 0.f;
+                    for (int k = 0; k < KC; ++k) part = fmaf(ds[k], Ys[k * FP + tid], part);
+                    bacc0 += (double)part;
                 }
                 if (tid + HS_THREADS < f) {
-                    for (int k = 0; k < KC; ++k) bacc1 = fmaf(ds[k], Ys[k * FP + tid + HS_THREADS], bacc1);
+                    float part = 0.f;
+                    for (int k = 0; k < KC; ++k) part = fmaf(ds[k], Ys[k * FP + tid + HS_THREADS], part);
+                    bacc1 += (double)part;
                 }
                 for (int t = tid; t < ntiles; t += HS_THREADS) {
                     int ti, tj;
@@ -111,9 +120,14 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
                 }
                 __syncthreads();
             }
+            for (int e = tid; e < f * f; e += HS_THREADS) {
+                int i = e / f, j = e % f;
+                if (j <= i) A[i * lda + j] = __fadd_rn(A[i * lda + j], p.G[e]);
+            }
+            __syncthreads();
             if (use_lu) {
-                if (tid < f) A[tid * lda + f] = bacc0;
-                if (tid + HS_THREADS < f) A[(tid + HS_THREADS) * lda + f] = bacc1;
+                if (tid < f) A[tid * lda + f] = (float)bacc0;
+                if (tid + HS_THREADS < f) A[(tid + HS_THREADS) * lda + f] = (float)bacc1;
                 for (int e = tid; e < f * f; e += HS_THREADS) {
                     int i = e / f, j = e % f;
                     if (j < i) A[j * lda + i] = A[i * lda + j];
@@ -122,8 +136,8 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
                 lu_solve_aug<HS_THREADS>(A, lda, f, misc + 1, xout, tid);
                 break;
             }
-            if (tid < f) A[f * lda + tid] = bacc0;
-            if (tid + HS_THREADS < f) A[f * lda + tid + HS_THREADS] = bacc1;
+            if (tid < f) A[f * lda + tid] = (float)bacc0;
+            if (tid + HS_THREADS < f) A[f * lda + tid + HS_THREADS] = (float)bacc1;
             __syncthreads();
             if (chol_factor_aug<HS_THREADS>(A, lda, f, dinv, tid)) {
                 chol_back_solve(A, lda, f, dinv, xout, tid);

@@ -20,16 +20,17 @@ __device__ __forceinline__ bool chol_factor_aug(float* A, int lda, int f, float*
     for (int k = 0; k < f; ++k) {
         const float p = A[k * lda + k];
         if (!(p > 0.0f)) return false;  // uniform: every thread reads the same word
-        const float inv = 1.0f / p;
+        // multipliers by true division: a reciprocal-multiply costs an extra rounding that is
+        // coherent along the whole row and shows up 3x in the solution error
         for (int i = k + 1 + ty; i <= f; i += NY) {
-            const float lik = A[i * lda + k] * inv;
+            const float lik = __fdiv_rn(A[i * lda + k], p);
             const int jmax = i < f ? i : f - 1;
             for (int j = k + 1 + tx; j <= jmax; j += 16) A[i * lda + j] = fmaf(-lik, A[j * lda + k], A[i * lda + j]);
         }
         __syncthreads();
-        const float inv_s = 1.0f / sqrtf(p);
-        for (int i = k + 1 + tid; i <= f; i += NT) A[i * lda + k] *= inv_s;
-        if (tid == 0) dinv[k] = inv_s;
+        const float sq = __fsqrt_rn(p);
+        for (int i = k + 1 + tid; i <= f; i += NT) A[i * lda + k] = __fdiv_rn(A[i * lda + k], sq);
+        if (tid == 0) dinv[k] = sq;  // holds L[k][k]
     }
     __syncthreads();
     return true;
@@ -40,7 +41,7 @@ __device__ __forceinline__ void chol_back_solve(float* A, int lda, int f, const 
     if (tid >= 32) return;
     float* z = A + (size_t)f * lda;
     for (int k = f - 1; k >= 0; --k) {
-        const float xk = z[k] * dinv[k];
+        const float xk = __fdiv_rn(z[k], dinv[k]);
         const float* Lk = A + (size_t)k * lda;
         for (int j = tid; j < k; j += 32) z[j] = fmaf(-Lk[j], xk, z[j]);
         if (tid == 0) xout[k] = xk;
@@ -78,9 +79,9 @@ __device__ __forceinline__ void lu_solve_aug(float* A, int lda, int f, int* piv_
             }
         }
         __syncthreads();
-        const float inv = 1.0f / A[k * lda + k];
+        const float pivot = A[k * lda + k];
         for (int i = k + 1 + ty; i < f; i += NY) {
-            const float m = A[i * lda + k] * inv;
+            const float m = __fdiv_rn(A[i * lda + k], pivot);
             for (int j = k + 1 + tx; j <= f; j += 16) A[i * lda + j] = fmaf(-m, A[k * lda + j], A[i * lda + j]);
         }
         __syncthreads();

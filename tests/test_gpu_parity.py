@@ -71,7 +71,7 @@ def test_gram_matches_fp64(cuda_device, n, f, ones):
     if ones:
         Y64[:, 0] = 1
     ref = Y64.T @ Y64 + 0.1 * np.eye(f)
-    assert np.max(np.abs(G - ref) / np.abs(ref).max()) < 2e-6
+    assert np.max(np.abs(G - ref) / np.abs(ref).max()) < 1.5e-7  # one fp32 rounding of the largest entry
     G2 = engine.gram(dev(Y, cuda_device), 0.1, ones_col0=ones).cpu().numpy()
     np.testing.assert_array_equal(G, G2)  # deterministic reduction order
 
@@ -121,14 +121,25 @@ def test_half_step_vs_oracle_realistic(cuda_device, users, items, nnz, dim, bias
     CT = C.T.tocsr()
     Y = orc.init_items(items, dim, bias)
     step = orc.half_step_bias if bias else orc.half_step
-    ref_u = step(Y, C, 0.1)
+    # First half-step from the all-positive U[0,1) initialisation: the worst-conditioned one.
+    # The reference's own fp32 arithmetic is 4e-5 (no bias) .. 1.2e-4 (bias) away from the fp64
+    # restatement here, so the bar is: no further from fp64 than max(1e-4, 2 x that noise), and
+    # within the same distance of the fp32 reference.
+    rows = slice(0, min(users, 1500))
+    ref_u = step(Y, C[rows], 0.1)
+    x64, tol = half_step_tol(Y, C[rows], ref_u, bias)
     X, _ = run_half_step(Y, C, bias, algo, cuda_device)
-    assert row_rel_err(X, ref_u) < HALF_STEP_TOL
-    # second half-step from the reference's users (mixed-sign factors, the steady-state regime)
+    err64, err32 = row_rel_err(X[rows], x64), row_rel_err(X[rows], ref_u)
+    print(f"first half-step: gpu-vs-fp64 {err64:.2e}, gpu-vs-ref32 {err32:.2e}, ref32-vs-fp64 tol {tol:.2e}")
+    assert err64 < tol and err32 < tol
+    # second half-step from mixed-sign factors (the steady-state regime): plain 1e-4
+    full_u = X if users <= 1500 else step(Y, C, 0.1)
     sel = slice(0, min(items, 800))
-    ref_i = step(ref_u, CT[sel], 0.1)
-    Xi, _ = run_half_step(ref_u, CT[sel], bias, algo, cuda_device)
-    assert row_rel_err(Xi, ref_i) < HALF_STEP_TOL
+    ref_i = step(full_u, CT[sel], 0.1)
+    Xi, _ = run_half_step(full_u, CT[sel], bias, algo, cuda_device)
+    err = row_rel_err(Xi, ref_i)
+    print(f"second half-step: gpu-vs-ref32 {err:.2e}")
+    assert err < HALF_STEP_TOL
 
 
 @pytest.mark.parametrize("algo_name,algo", ALGOS)
@@ -163,6 +174,8 @@ def test_half_step_edge_rows(cuda_device, f, bias, algo_name, algo):
 @pytest.mark.parametrize("algo_name,algo", ALGOS)
 def test_half_step_indefinite_falls_back_to_lu(cuda_device, algo_name, algo):
     """Negative confidence weights make A indefinite; the reference's sgesv still solves it."""
+    if algo == _lib.ALGO_TCGEN05 and not tc_supported(64, False):
+        pytest.skip("shape not taken by the tcgen05 path")
     rng = np.random.default_rng(5)
     N, f = 400, 64
     C = scipy.sparse.random(40, N, density=0.2, format="csr", dtype=np.float32, random_state=3)
@@ -189,6 +202,8 @@ def test_half_step_full_size_properties(cuda_device):
     X = engine.half_step(Cd, Yd, G).cpu().numpy()
     assert np.all(np.isfinite(X))
     G64 = Y.astype(np.float64).T @ Y.astype(np.float64) + 0.1 * np.eye(f)
+    G32 = np.dot(Y.T, Y) + np.float32(0.1) * np.eye(f, dtype=np.float32)
+    worst = worst_noise = 0.0
     rows = np.concatenate([np.random.default_rng(1).integers(0, users, 48), [int(np.argmax(np.diff(C.indptr)))]])
     for r in rows:
         lo, hi = C.indptr[r], C.indptr[r + 1]
@@ -199,7 +214,14 @@ def test_half_step_full_size_properties(cuda_device):
         d = C.data[lo:hi].astype(np.float64)
         A = G64 + (Yr * d[:, None]).T @ Yr
         x = np.linalg.solve(A, (d + 1) @ Yr)
-        assert np.linalg.norm(X[r] - x) / np.linalg.norm(x) < HALF_STEP_TOL
+        # the reference's own fp32 arithmetic for this row (np.dot / sgesv), as the noise yardstick
+        Yr32 = Y[C.indices[lo:hi]]
+        x32 = np.linalg.solve(np.dot(Yr32.T, Yr32 * C.data[lo:hi, None]) + G32, np.dot(C.data[lo:hi] + 1, Yr32))
+        noise = np.linalg.norm(x32 - x) / np.linalg.norm(x)
+        worst_noise = max(worst_noise, noise)
+        worst = max(worst, np.linalg.norm(X[r] - x) / np.linalg.norm(x))
+    print(f"full size: worst gpu-vs-fp64 {worst:.2e}; reference fp32-vs-fp64 on the same rows {worst_noise:.2e}")
+    assert worst < max(HALF_STEP_TOL, 2 * worst_noise)
     X2 = engine.half_step(Cd, Yd, G).cpu().numpy()
     np.testing.assert_array_equal(X, X2)
     half = users // 2
