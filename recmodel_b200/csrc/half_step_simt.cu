@@ -39,6 +39,7 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
                         : reinterpret_cast<float*>(misc + 4);
     const int T = FP / 4;
     const int ntiles = T * (T + 1) / 2;
+    if (p.run_if != nullptr && *p.run_if == 0) return;  // fix-up launch with nothing to fix
 
     while (true) {
         if (tid == 0) misc[0] = atomicAdd(p.counter, 1);
@@ -175,7 +176,7 @@ static SimtPlan simt_plan(int f) {
     return pl;
 }
 
-size_t simt_half_step_workspace_bytes(int f) {
+size_t simt_half_step_workspace_bytes(int f) {  // 256-byte header (row counter, flags) + slabs
     SimtPlan pl = simt_plan(f);
     return 256 + pl.slab_bytes * pl.grid;
 }
@@ -189,11 +190,12 @@ int simt_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStre
     }
     HalfStepParams p = in;
     p.counter = reinterpret_cast<int*>(ws);
+    const bool fixup = in.run_if != nullptr;  // header already initialised by the caller
     p.slab = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256);
     p.lda = pl.lda;
     p.FP = pl.FP;
     p.KC = pl.KC;
-    WMF_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+    if (!fixup) WMF_CUDA(cudaMemsetAsync(ws, 0, 256, st));
     int grid = pl.grid;
     if ((int64_t)grid > in.rows) grid = (int)in.rows;
     if (pl.a_global) {

@@ -13,8 +13,20 @@
 
 namespace wmf {
 
-template <int NT>
-__device__ __forceinline__ bool chol_factor_aug(float* A, int lda, int f, float* dinv, int tid) {
+// Barrier over the threads that run the solve: the whole CTA (SIMT kernel) or a named
+// barrier over the solver warps only (warp-specialised tcgen05 kernel).
+struct BlockSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <int ID, int NTHREADS>
+struct NamedSync {
+    __device__ __forceinline__ void operator()() const {
+        asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory");
+    }
+};
+
+template <int NT, class Sync = BlockSync>
+__device__ __forceinline__ bool chol_factor_aug(float* A, int lda, int f, float* dinv, int tid, Sync sync = Sync()) {
     constexpr int NY = NT / 16;
     const int ty = tid / 16, tx = tid % 16;
     for (int k = 0; k < f; ++k) {
@@ -27,12 +39,12 @@ __device__ __forceinline__ bool chol_factor_aug(float* A, int lda, int f, float*
             const int jmax = i < f ? i : f - 1;
             for (int j = k + 1 + tx; j <= jmax; j += 16) A[i * lda + j] = fmaf(-lik, A[j * lda + k], A[i * lda + j]);
         }
-        __syncthreads();
+        sync();
         const float sq = __fsqrt_rn(p);
         for (int i = k + 1 + tid; i <= f; i += NT) A[i * lda + k] = __fdiv_rn(A[i * lda + k], sq);
         if (tid == 0) dinv[k] = sq;  // holds L[k][k]
     }
-    __syncthreads();
+    sync();
     return true;
 }
 
