@@ -19,6 +19,7 @@ struct HalfStepParams {
     int64_t ldx;
     // filled by the implementation
     int* counter;
+    long long* prof;    // nullable: per-role cycle counters of CTA 0 (tcgen05 kernel, debugging)
     const int* run_if;  // nullable: the SIMT kernel returns at once when *run_if == 0
     float* slab;
     int lda;

@@ -28,9 +28,11 @@
 //
 // Rows whose weights are negative (sqrt undefined) or whose Cholesky meets a non-positive
 // pivot raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).
+#include <stdlib.h>
 #include "common.cuh"
 #include "half_step.cuh"
 #include "solve.cuh"
+#include "solve128.cuh"
 
 namespace wmf {
 
@@ -38,25 +40,29 @@ namespace tc {
 
 constexpr int F = 128;               // factor width handled by this kernel
 constexpr int CHUNK = 32;            // stored entries per staged tile (= one 128-byte swizzle row)
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 2;
 constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 32 fp32 (K) = 16 KB
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // [zh ; zl]
-constexpr int LDA = F + 1;           // 129: odd leading dimension, conflict-free both ways
-constexpr int GATHER_THREADS = 128, MMA_WARP = 4, SOLVER_THREADS = 256;
+constexpr int NGROUP = 2;            // solver groups, each 128 threads on its own row
+constexpr int GATHER_THREADS = 128, MMA_WARP = 4, SOLVER_THREADS = NGROUP * s128::GROUP;
 constexpr int THREADS = GATHER_THREADS + 32 + SOLVER_THREADS;  // 416
-constexpr int SOLVER_BAR_ID = 1;
 constexpr uint32_t TMEM_COLS = 512;
 
 // shared memory carve-up (bytes from a 1024-aligned base)
 constexpr int OFF_STAGES = 0;
-constexpr int OFF_A = OFF_STAGES + NSTAGE * STAGE_BYTES;            // (F+1) x LDA floats
-constexpr int A_BYTES = ((F + 1) * LDA * 4 + 15) / 16 * 16;
-constexpr int OFF_BVEC = OFF_A + A_BYTES;                           // 2 x F floats
-constexpr int OFF_DIAG = OFF_BVEC + 2 * F * 4;                      // F floats
-constexpr int OFF_BARS = OFF_DIAG + F * 4;                          // mbarriers (8 B each)
+constexpr int OFF_A = OFF_STAGES + NSTAGE * STAGE_BYTES;            // NGROUP x (132 x 132 floats)
+constexpr int A_BYTES = s128::A_FLOATS * 4;
+constexpr int OFF_LPT = OFF_A + NGROUP * A_BYTES;                   // NGROUP x (8 x 132 floats)
+constexpr int LPT_BYTES = s128::LPT_FLOATS * 4;
+constexpr int OFF_DINV = OFF_LPT + NGROUP * LPT_BYTES;              // NGROUP x F floats
+constexpr int OFF_XS = OFF_DINV + NGROUP * F * 4;                   // NGROUP x F floats
+constexpr int OFF_BVEC = OFF_XS + NGROUP * F * 4;                   // 2 x F floats
+constexpr int OFF_BARS = OFF_BVEC + 2 * F * 4;                      // mbarriers (8 B each)
 constexpr int NBARS = 2 * NSTAGE + 8;
 constexpr int OFF_TMEM_PTR = OFF_BARS + NBARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                // + slack for alignment
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(OFF_A % 16 == 0 && OFF_LPT % 16 == 0 && OFF_DINV % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -131,9 +137,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
-    float* A = reinterpret_cast<float*>(smem + OFF_A);
     float* bvec = reinterpret_cast<float*>(smem + OFF_BVEC);
-    float* diag = reinterpret_cast<float*>(smem + OFF_DIAG);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
     const uint32_t bars = smem_base + OFF_BARS;
     // barrier ids
@@ -150,9 +154,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), GATHER_THREADS); mbar_init(bar_empty(s), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_acc_full(b), 1);
-            mbar_init(bar_acc_empty(b), SOLVER_THREADS);
+            mbar_init(bar_acc_empty(b), s128::GROUP);
             mbar_init(bar_b_full(b), GATHER_THREADS);
-            mbar_init(bar_b_empty(b), SOLVER_THREADS);
+            mbar_init(bar_b_empty(b), s128::GROUP);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -171,86 +175,142 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
 
     if (warp < 4) {
         // =============================== GATHER ===============================
+        // Software pipeline over the CTA's flattened (row, chunk) sequence: while chunk c is
+        // scaled/split/stored, the 32 factor loads of chunk c+1 and the index/weight loads of
+        // chunk c+2 are already in flight.
         const int m = tid;  // feature index
-        uint32_t chunk_n = 0, row_n = 0;
-        bool saw_negative = false;
-        for (int64_t r = first; r < rows; r += step) {
-            const int64_t row = p.row_order ? p.row_order[r] : r;
-            const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-            if (lo == hi) continue;
-            double bacc = 0.0;
-            for (int64_t base = lo; base < hi; base += CHUNK, ++chunk_n) {
-                const int s = chunk_n % NSTAGE;
-                const uint32_t ph = (chunk_n / NSTAGE) & 1u;
-                // this lane's entry of the chunk (every warp keeps its own copy: no cross-warp sync)
-                const int64_t e = base + lane;
-                int64_t off = 0;
-                float sq = 0.f, dp1 = 0.f;
-                if (e < hi) {
-                    const float d = p.data[e];
-                    off = (int64_t)p.indices[e] * p.ldy;
-                    if (d < 0.f) saw_negative = true;
-                    sq = sqrtf(fabsf(d));
-                    dp1 = __fadd_rn(d, 1.0f);
-                }
-                // issue all 32 factor loads first (32 independent 128-B lines per warp in flight)
-                float v[CHUNK];
-#pragma unroll
-                for (int j = 0; j < CHUNK; ++j) {
-                    const int64_t oj = __shfl_sync(0xffffffffu, off, j);
-                    v[j] = __ldg(p.Y + oj + m);
-                }
-                mbar_wait(bar_empty(s), ph ^ 1u);
-                uint8_t* tile_h = smem + OFF_STAGES + s * STAGE_BYTES + m * 128;
-                uint8_t* tile_l = tile_h + TILE_BYTES;
-                float part = 0.f;
-#pragma unroll
-                for (int g = 0; g < CHUNK / 4; ++g) {
-                    float zh[4], zl[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = g * 4 + jj;
-                        const float sj = __shfl_sync(0xffffffffu, sq, j);
-                        const float cj = __shfl_sync(0xffffffffu, dp1, j);
-                        const float z = sj * v[j];
-                        zh[jj] = tf32_round(z);
-                        zl[jj] = tf32_round(z - zh[jj]);
-                        part = fmaf(cj, v[j], part);
-                    }
-                    const int sw = (g ^ (m & 7)) << 4;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-                    *reinterpret_cast<float4*>(tile_h + sw) = make_float4(zh[0], zh[1], zh[2], zh[3]);
-                    *reinterpret_cast<float4*>(tile_l + sw) = make_float4(zl[0], zl[1], zl[2], zl[3]);
-                }
-                bacc += (double)part;
-                fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-                mbar_arrive(bar_full(s));
+        struct Cursor {
+            int64_t r, base, hi;  // position in the CTA's row list, first entry of the chunk, row end
+        };
+        auto seek = [&](Cursor& c) {  // move c.r forward to the next non-empty row (or past the end)
+            while (c.r < rows) {
+                const int64_t row = p.row_order ? p.row_order[c.r] : c.r;
+                const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
+                if (lo != hi) { c.base = lo; c.hi = hi; return; }
+                c.r += step;
             }
-            const int b = row_n & 1;
-            const uint32_t bph = (row_n >> 1) & 1u;
-            mbar_wait(bar_b_empty(b), bph ^ 1u);
-            bvec[b * F + m] = (float)bacc;
-            mbar_arrive(bar_b_full(b));
-            ++row_n;
+        };
+        auto advance = [&](Cursor& c) {
+            c.base += CHUNK;
+            if (c.base >= c.hi) { c.r += step; seek(c); }
+        };
+        // raw index/weight of this lane's entry: loaded two chunks ahead, first touched one chunk
+        // later (the in-order pipe would otherwise stall on the load right here)
+        struct Raw { int idx; float d; };
+        struct Meta { int64_t off; float sq, dp1; };
+        bool saw_negative = false;
+        auto load_raw = [&](const Cursor& c) {
+            Raw rw{-1, 0.f};
+            if (c.r < rows) {
+                const int64_t e = c.base + lane;
+                if (e < c.hi) { rw.d = __ldg(p.data + e); rw.idx = __ldg(p.indices + e); }
+            }
+            return rw;
+        };
+        auto to_meta = [&](const Raw& rw) {
+            Meta mt{0, 0.f, 0.f};
+            if (rw.idx >= 0) {
+                mt.off = (int64_t)rw.idx * p.ldy;
+                if (rw.d < 0.f) saw_negative = true;
+                mt.sq = sqrtf(fabsf(rw.d));
+                mt.dp1 = __fadd_rn(rw.d, 1.0f);
+            }
+            return mt;
+        };
+        Cursor c0{first, 0, 0};
+        seek(c0);
+        Cursor c1 = c0;
+        if (c1.r < rows) advance(c1);
+        Cursor c2 = c1;
+        if (c2.r < rows) advance(c2);
+        Meta m0 = to_meta(load_raw(c0));
+        Raw r1 = load_raw(c1);
+        float v0[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) v0[j] = __ldg(p.Y + __shfl_sync(0xffffffffu, m0.off, j) + m);
+        uint32_t chunk_n = 0, row_n = 0;
+        double bacc = 0.0;
+        const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        long long t_empty = 0, t_bempty = 0, t_start = prof ? clock64() : 0, tt = 0;
+        while (c0.r < rows) {
+            // issue the next chunk's factor loads and the chunk-after-next's index loads
+            const Meta m1 = to_meta(r1);  // loaded one iteration ago
+            float v1[CHUNK];
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) v1[j] = __ldg(p.Y + __shfl_sync(0xffffffffu, m1.off, j) + m);
+            const Raw r2 = load_raw(c2);  // first use: next iteration
+            const int s = chunk_n % NSTAGE;
+            const uint32_t ph = (chunk_n / NSTAGE) & 1u;
+            if (prof) tt = clock64();
+            mbar_wait(bar_empty(s), ph ^ 1u);
+            if (prof) t_empty += clock64() - tt;
+            uint8_t* tile_h = smem + OFF_STAGES + s * STAGE_BYTES + m * 128;
+            uint8_t* tile_l = tile_h + TILE_BYTES;
+            float part = 0.f;
+#pragma unroll
+            for (int g = 0; g < CHUNK / 4; ++g) {
+                float zh[4], zl[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = g * 4 + jj;
+                    const float sj = __shfl_sync(0xffffffffu, m0.sq, j);
+                    const float cj = __shfl_sync(0xffffffffu, m0.dp1, j);
+                    const float z = sj * v0[j];
+                    zh[jj] = tf32_round(z);
+                    zl[jj] = tf32_round(z - zh[jj]);
+                    part = fmaf(cj, v0[j], part);
+                }
+                const int sw = (g ^ (m & 7)) << 4;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+                *reinterpret_cast<float4*>(tile_h + sw) = make_float4(zh[0], zh[1], zh[2], zh[3]);
+                *reinterpret_cast<float4*>(tile_l + sw) = make_float4(zl[0], zl[1], zl[2], zl[3]);
+            }
+            bacc += (double)part;
+            fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(bar_full(s));
+            ++chunk_n;
+            if (c0.base + CHUNK >= c0.hi) {  // last chunk of its row: hand the rhs to the solver group
+                const int b = row_n & 1;
+                const uint32_t bph = (row_n >> 1) & 1u;
+                if (prof) tt = clock64();
+                mbar_wait(bar_b_empty(b), bph ^ 1u);
+                if (prof) t_bempty += clock64() - tt;
+                bvec[b * F + m] = (float)bacc;
+                mbar_arrive(bar_b_full(b));
+                bacc = 0.0;
+                ++row_n;
+            }
+            c0 = c1; c1 = c2;
+            if (c2.r < rows) advance(c2);
+            m0 = m1; r1 = r2;
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) v0[j] = v1[j];
         }
         if (saw_negative) atomicOr(flags, 1);
+        if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = chunk_n; p.prof[4] = row_n; }
     } else if (warp == MMA_WARP) {
         // =============================== MMA ISSUE ===============================
         if (lane == 0) {
             uint32_t chunk_n = 0, row_n = 0;
+            const bool prof = p.prof != nullptr && blockIdx.x == 0;
+            long long t_full = 0, t_accempty = 0, t_start = prof ? clock64() : 0, tt = 0;
             for (int64_t r = first; r < rows; r += step) {
                 const int64_t row = p.row_order ? p.row_order[r] : r;
                 const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
                 if (lo == hi) continue;
                 const int b = row_n & 1;
                 const uint32_t aph = (row_n >> 1) & 1u;
+                if (prof) tt = clock64();
                 mbar_wait(bar_acc_empty(b), aph ^ 1u);
+                if (prof) t_accempty += clock64() - tt;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256);
                 uint32_t accumulate = 0;
                 for (int64_t base = lo; base < hi; base += CHUNK, ++chunk_n) {
                     const int s = chunk_n % NSTAGE;
                     const uint32_t ph = (chunk_n / NSTAGE) & 1u;
+                    if (prof) tt = clock64();
                     mbar_wait(bar_full(s), ph);
+                    if (prof) t_full += clock64() - tt;
                     tc_fence_after();
                     const int kc = (int)((hi - base) < CHUNK ? (hi - base) : CHUNK);
                     const int nk = (kc + 7) >> 3;
@@ -267,47 +327,71 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                 tc_commit(bar_acc_full(b));
                 ++row_n;
             }
+            if (prof) { p.prof[8] = clock64() - t_start; p.prof[9] = t_full; p.prof[10] = t_accempty; }
         }
     } else {
         // =============================== SOLVE ===============================
-        const int st = tid - (GATHER_THREADS + 32);  // 0..255
-        const int q = warp & 3;                      // TMEM lane quarter this warp may read
-        const int half = (warp - 5) >> 2;            // which 64-column half it converts
-        const int i = q * 32 + lane;                 // matrix row held by this thread
-        NamedSync<SOLVER_BAR_ID, SOLVER_THREADS> sync;
+        // Two groups of 128 threads; group g owns the CTA's non-empty rows with (row_n & 1) == g,
+        // which is also the accumulator buffer it drains.
+        const int g = (warp - 5) >> 2;
+        const int q = warp & 3;        // TMEM lane quarter this warp may read
+        const int i = q * 32 + lane;   // matrix row owned by this thread (0..127)
+        float* A = reinterpret_cast<float*>(smem + OFF_A + g * A_BYTES);
+        float* LpT = reinterpret_cast<float*>(smem + OFF_LPT + g * LPT_BYTES);
+        float* dinv = reinterpret_cast<float*>(smem + OFF_DINV + g * F * 4);
+        float* xs = reinterpret_cast<float*>(smem + OFF_XS + g * F * 4);
+        constexpr int LDA = s128::LDA;
+        auto gsync = [&]() {
+            if (g == 0) s128::group_sync<1>(); else s128::group_sync<2>();
+        };
         uint32_t row_n = 0;
+        const bool prof = p.prof != nullptr && blockIdx.x == 0 && g == 0 && i == 0;
+        long long t_accfull = 0, t_drain = 0, t_g = 0, t_bfull = 0, t_solve = 0, t_start = prof ? clock64() : 0, tt = 0;
         for (int64_t r = first; r < rows; r += step) {
             const int64_t row = p.row_order ? p.row_order[r] : r;
             const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
             float* xout = p.X + row * p.ldx;
             if (lo == hi) {  // wmf_model.py:223-225
-                for (int c = st; c < F; c += SOLVER_THREADS) xout[c] = 0.0f;
+                if (g == 0) xout[i] = 0.0f;
                 continue;
             }
             const int b = row_n & 1;
             const uint32_t ph = (row_n >> 1) & 1u;
+            ++row_n;
+            if (b != g) continue;
+            if (prof) tt = clock64();
             mbar_wait(bar_acc_full(b), ph);
+            if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
-            // phase 1: own row, lower part: A[i][j] = P[i][j] + Q[i][j]   (j <= i)
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                const int col0 = half * 64 + cb * 32;
+            // phase 1: own row: A[i][j] = P[i][j] + Q[i][j] (j < i), P + 2Q on the diagonal
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                const int col0 = cb * 32;
+                if (col0 > i) break;  // nothing at or left of the diagonal in this block (warp-uniform: i>>5)
                 float pv[32], qv[32];
                 tmem_ld32(t_row + col0, pv);
                 tmem_ld32(t_row + 128 + col0, qv);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int j = col0 + c;
-                    if (j < i) A[i * LDA + j] = pv[c] + qv[c];
-                    else if (j == i) A[i * LDA + j] = pv[c] + 2.0f * qv[c];  // diagonal: Q + Q^T
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int j0 = col0 + c4 * 4;
+                    if (j0 <= i) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float qq = qv[c4 * 4 + e];
+                            o[e] = pv[c4 * 4 + e] + qq + ((j0 + e == i) ? qq : 0.0f);
+                        }
+                        *reinterpret_cast<float4*>(A + i * LDA + j0) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
                 }
             }
-            sync();
-            // phase 2: transposed part: A[j][i] += Q[i][j]   (j > i); one writer per element
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                const int col0 = half * 64 + cb * 32;
+            gsync();
+            // phase 2: transposed part: A[j][i] += Q[i][j] (j > i); exactly one writer per element
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                const int col0 = cb * 32;
+                if (col0 + 31 <= (i & ~31)) continue;  // whole block at or left of this warp's rows (warp-uniform)
                 float qv[32];
                 tmem_ld32(t_row + 128 + col0, qv);
 #pragma unroll
@@ -318,25 +402,47 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
             }
             tc_fence_before();
             mbar_arrive(bar_acc_empty(b));  // the tensor core may start the row after next
-            sync();
-            // + G once (wmf_model.py:239 adds YTY_I to the finished weighted Gram), rhs into row F
-            for (int e = st; e < F * F; e += SOLVER_THREADS) {
-                const int ii = e >> 7, jj = e & (F - 1);
-                if (jj <= ii) A[ii * LDA + jj] = __fadd_rn(A[ii * LDA + jj], __ldg(p.G + e));
+            gsync();
+            if (prof) { t_drain += clock64() - tt; tt = clock64(); }
+            // + G once (wmf_model.py:239 adds YTY_I to the finished weighted Gram), rhs into row 128
+            // (batches of 8 independent 16-byte loads: G lives in L2, one exposed latency per batch)
+#pragma unroll 1
+            for (int e0 = i; e0 < F * (F / 4); e0 += s128::GROUP * 8) {
+                float4 gv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e4 = e0 + u * s128::GROUP;
+                    const int rr = e4 >> 5, c4 = (e4 & 31) * 4;
+                    gv[u] = (c4 <= rr) ? __ldg(reinterpret_cast<const float4*>(p.G + rr * F + c4)) : make_float4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e4 = e0 + u * s128::GROUP;
+                    const int rr = e4 >> 5, c4 = (e4 & 31) * 4;
+                    if (c4 <= rr) {
+                        float4* dst = reinterpret_cast<float4*>(A + rr * LDA + c4);
+                        float4 v = *dst;
+                        v.x = __fadd_rn(v.x, gv[u].x); v.y = __fadd_rn(v.y, gv[u].y);
+                        v.z = __fadd_rn(v.z, gv[u].z); v.w = __fadd_rn(v.w, gv[u].w);
+                        *dst = v;
+                    }
+                }
             }
+            if (prof) { t_g += clock64() - tt; tt = clock64(); }
             mbar_wait(bar_b_full(b), ph);
-            if (st < F) A[F * LDA + st] = bvec[b * F + st];
+            if (prof) { t_bfull += clock64() - tt; tt = clock64(); }
+            A[F * LDA + i] = bvec[b * F + i];
             mbar_arrive(bar_b_empty(b));
-            sync();
-            const bool ok = chol_factor_aug<SOLVER_THREADS>(A, LDA, F, diag, st, sync);
-            if (ok) {
-                chol_back_solve(A, LDA, F, diag, xout, st);
-            } else if (st == 0) {
-                atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
-            }
-            sync();
-            ++row_n;
+            gsync();
+            bool ok;
+            if (g == 0) ok = s128::chol_solve_128<1>(A, LpT, dinv, xs, i);
+            else ok = s128::chol_solve_128<2>(A, LpT, dinv, xs, i);
+            if (ok) xout[i] = xs[i];
+            else if (i == 0) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
+            gsync();
+            if (prof) t_solve += clock64() - tt;
         }
+        if (prof) { p.prof[16] = clock64() - t_start; p.prof[17] = t_accfull; p.prof[18] = t_drain; p.prof[19] = t_g; p.prof[20] = t_bfull; p.prof[21] = t_solve; p.prof[22] = row_n; }
     }
     // =============================== TEARDOWN ===============================
     tc_fence_before();
@@ -361,6 +467,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     int* flags = reinterpret_cast<int*>(ws) + 1;  // [0] = SIMT row counter, [1] = redo flags
     WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     HalfStepParams p = in;
+    p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 64) : nullptr;
     int grid = sm_count();
     if ((int64_t)grid > in.rows) grid = (int)in.rows;
     als_half_step_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, flags);

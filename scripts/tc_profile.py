@@ -1,0 +1,29 @@
+"""Per-role cycle breakdown of CTA 0 of the tcgen05 half-step kernel (WMF_TC_PROFILE=1)."""
+import os, sys
+os.environ["WMF_TC_PROFILE"] = "1"
+sys.path.insert(0, ".")
+import numpy as np, torch
+from oracle import wmf_oracle as orc
+from recmodel_b200 import engine, _lib
+from recmodel_b200.engine import DeviceCSR
+from recmodel_b200.synthetic import make_counts_cached
+C = make_counts_cached(138493, 26744, 20_000_000)
+dev = torch.device("cuda:0")
+Cd = DeviceCSR.from_scipy(C, dev); engine.preprocess_(Cd.data, "log", 10, 1); CT = Cd.transpose()
+Y = torch.from_numpy(orc.init_items(26744, 128, False)).to(dev)
+def run(csr, Yd, name):
+    G = engine.gram(Yd, 0.1)
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); X = engine.half_step(csr, Yd, G, algo=_lib.ALGO_TCGEN05); e1.record(); torch.cuda.synchronize()
+    ws = engine.workspace(0, dev)
+    prof = ws[64:256].view(torch.int64).cpu().numpy()
+    ms = e0.elapsed_time(e1)
+    print(f"{name}: {ms:.2f} ms")
+    f = lambda c: f"{c/1.965e6:.2f}ms"
+    print("  gather total", f(prof[0]), "wait_empty", f(prof[1]), "wait_bempty", f(prof[2]), "chunks", prof[3], "rows", prof[4])
+    print("  mma total", f(prof[8]), "wait_full", f(prof[9]), "wait_accempty", f(prof[10]))
+    print("  solver0 total", f(prof[16]), "wait_accfull", f(prof[17]), "drain", f(prof[18]), "G", f(prof[19]), "wait_bfull", f(prof[20]), "solve", f(prof[21]), "rows", prof[22])
+    return X
+U = run(Cd, Y, "user half-step")
+run(CT, U, "item half-step")
