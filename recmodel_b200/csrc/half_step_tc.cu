@@ -2,37 +2,36 @@
 // Replaces the per-row loop of recompute_factors (wmf_model.py:220-239).
 //
 // Per CSR row r:  A_r = G + sum_j d_j y_j y_j^T  (128x128, K = n_r),  b_r = sum_j (d_j+1) y_j,
-// x_r = A_r^-1 b_r. The K-loop runs on the 5th-gen tensor cores with FP32-equivalent accuracy:
+// x_r = A_r^-1 b_r.  Everything O(f^2) per entry and O(f^3) per row runs on the 5th-gen tensor
+// cores with FP32-equivalent accuracy (3xTF32: plain TF32 fails the 1e-4 bar):
 //
-//   z_j = sqrt(d_j) y_j,  z = zh + zl  (zh, zl exactly representable in TF32, zl = z - zh)
-//   sum_j z_j z_j^T ~= P + Q + Q^T,   P = sum zh zh^T,  Q = sum zh zl^T         (3xTF32 with
-//   the symmetric pair folded: the dropped term zl zl^T is 2^-22 relative)
+//   Gram      z_j = sqrt(d_j) y_j = zh + zl (both TF32-exact);  W = sum zh zh^T + zh zl^T + zl zh^T
+//             -> three tcgen05.mma (kind::tf32, M=N=128, K=8) per 8 stored entries into a
+//             128-column fp32 TMEM accumulator; operand tiles K-major, 128-byte swizzled.
+//   Cholesky  the matrix STAYS in TMEM. Panels of 8 columns: each thread (= TMEM lane = matrix
+//             row) loads its 8 panel entries (tcgen05.ld), adds G lazily, the 8x8 diagonal block
+//             is factored in registers, the row is solved against it, the panel L (hi/lo split)
+//             goes to shared memory as an MMA operand and the rank-8 trailing update
+//             S -= L L^T is again three tcgen05.mma (negated A) on the whole 128x128 accumulator.
+//             The right-hand side rides along in registers (forward substitution fused);
+//             the finished L is written back over the dead columns (tcgen05.st) and read once
+//             more, 8 rows at a time, for the back substitution.
 //
-// so ONE tcgen05.mma (kind::tf32, M=128, N=256, K=8) per 8 stored entries produces [P | Q] in
-// a 256-column fp32 TMEM accumulator: A-operand = the zh tile, B-operand = [zh ; zl] tiles.
-// Plain single-pass TF32 fails the 1e-4 parity bar; this split passes it.
-//
+// TMEM holds four such matrices (4 x 128 = 512 columns): four solver groups of 128 threads each
+// own one accumulator, so while one row is in its pivot chain three others fill the issue slots.
 // One persistent CTA per SM, warp-specialised, all hand-offs through mbarriers:
-//   warps 0-3  gather  thread m owns feature m: per 32-entry chunk it loads Y[idx_j][m] (one
-//              coalesced 128-B line per warp and entry), forms zh/zl and stores them K-major
-//              into a 128B-swizzled shared-memory tile (what a TMA load would have produced;
-//              the operand is a gather + scale + split, which TMA cannot do), and keeps the
-//              rhs b[m] in registers.
-//   warp 4     MMA     one thread issues tcgen05.mma over the staged tiles, commits to the
-//              stage's "empty" barrier and, after the last chunk, to the accumulator's "full".
-//   warps 5-12 solve   tcgen05.ld the accumulator, form the lower triangle of
-//              A = (P + Q + Q^T) + G in shared memory, release the accumulator, then Cholesky
-//              (forward substitution fused as an extra row) + back substitution, write x_r.
-// The accumulator is double-buffered (2 x 256 = all 512 TMEM columns) so the tensor core
-// works on row r+1 while row r is being solved.
+//   warps 0-3   gather   thread m owns feature m: loads Y[idx_j][m] for 32 entries (one coalesced
+//               128-B line per warp and entry), forms zh/zl, stores them with the XOR swizzle a TMA
+//               load would have produced (TMA cannot: the operand is gathered, scaled and split),
+//               keeps the rhs b[m] in registers.
+//   warps 4-19  solve    group g = (warp-4)/4 owns accumulator g and the rows n with n % 4 == g.
+//   warp 20     MMA      one thread issues the Gram MMAs and commits stage/accumulator barriers.
 //
 // Rows whose weights are negative (sqrt undefined) or whose Cholesky meets a non-positive
 // pivot raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).
 #include <stdlib.h>
 #include "common.cuh"
 #include "half_step.cuh"
-#include "solve.cuh"
-#include "solve128.cuh"
 
 namespace wmf {
 
@@ -40,29 +39,42 @@ namespace tc {
 
 constexpr int F = 128;               // factor width handled by this kernel
 constexpr int CHUNK = 32;            // stored entries per staged tile (= one 128-byte swizzle row)
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 3;            // operand-tile stages
+constexpr int NSTG = 3;              // raw gather staging buffers (cp.async depth)
 constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 32 fp32 (K) = 16 KB
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // [zh ; zl]
-constexpr int NGROUP = 2;            // solver groups, each 128 threads on its own row
-constexpr int GATHER_THREADS = 128, MMA_WARP = 4, SOLVER_THREADS = NGROUP * s128::GROUP;
-constexpr int THREADS = GATHER_THREADS + 32 + SOLVER_THREADS;  // 416
+constexpr int STG_BYTES = CHUNK * F * 4;     // 32 gathered factor rows, row-major, 16 KB
+constexpr int NB = 8;                // Cholesky panel width
+constexpr int NGROUP = 4;            // solver groups = TMEM accumulators
+constexpr int GROUP = 128;
+constexpr int GATHER_THREADS = 128;
+constexpr int SOLVER_WARP0 = 4, MMA_WARP = SOLVER_WARP0 + NGROUP * 4;
+constexpr int THREADS = (MMA_WARP + 1) * 32;               // 672
 constexpr uint32_t TMEM_COLS = 512;
+static_assert(NGROUP * F <= 512, "TMEM columns");
+
+// per-group shared memory
+constexpr int PANEL_TILE_BYTES = F * NB * 4;          // 4 KB: 128 rows x 8 fp32, K-major, no swizzle
+constexpr int G_OFF_TILEH = 0;
+constexpr int G_OFF_TILEL = G_OFF_TILEH + PANEL_TILE_BYTES;
+constexpr int G_OFF_DBLK = G_OFF_TILEL + PANEL_TILE_BYTES;          // 2 x (8 x 8) floats
+constexpr int G_OFF_BBLK = G_OFF_DBLK + 2 * NB * NB * 4;            // 2 x 8 floats (rhs / z of the block)
+constexpr int G_OFF_RED = G_OFF_BBLK + 2 * NB * 4;                  // 2 x 4 warps x 8 floats
+constexpr int G_OFF_DINV = G_OFF_RED + 2 * 4 * NB * 4;              // 128 floats
+constexpr int GROUP_BYTES = ((G_OFF_DINV + F * 4 + 127) / 128) * 128;
 
 // shared memory carve-up (bytes from a 1024-aligned base)
 constexpr int OFF_STAGES = 0;
-constexpr int OFF_A = OFF_STAGES + NSTAGE * STAGE_BYTES;            // NGROUP x (132 x 132 floats)
-constexpr int A_BYTES = s128::A_FLOATS * 4;
-constexpr int OFF_LPT = OFF_A + NGROUP * A_BYTES;                   // NGROUP x (8 x 132 floats)
-constexpr int LPT_BYTES = s128::LPT_FLOATS * 4;
-constexpr int OFF_DINV = OFF_LPT + NGROUP * LPT_BYTES;              // NGROUP x F floats
-constexpr int OFF_XS = OFF_DINV + NGROUP * F * 4;                   // NGROUP x F floats
-constexpr int OFF_BVEC = OFF_XS + NGROUP * F * 4;                   // 2 x F floats
-constexpr int OFF_BARS = OFF_BVEC + 2 * F * 4;                      // mbarriers (8 B each)
-constexpr int NBARS = 2 * NSTAGE + 8;
+constexpr int OFF_STG = OFF_STAGES + NSTAGE * STAGE_BYTES;
+constexpr int OFF_META = OFF_STG + NSTG * STG_BYTES;                // NSTG x 32 x float2
+constexpr int OFF_GROUPS = OFF_META + NSTG * CHUNK * 8;
+constexpr int OFF_BVEC = OFF_GROUPS + NGROUP * GROUP_BYTES;         // NGROUP x F floats
+constexpr int OFF_BARS = OFF_BVEC + NGROUP * F * 4;                 // mbarriers (8 B each)
+constexpr int NBARS = 2 * NSTAGE + NSTG + 5 * NGROUP;
 constexpr int OFF_TMEM_PTR = OFF_BARS + NBARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                // + slack for alignment
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_A % 16 == 0 && OFF_LPT % 16 == 0 && OFF_DINV % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
+static_assert(OFF_GROUPS % 128 == 0 && GROUP_BYTES % 128 == 0 && OFF_BARS % 8 == 0 && OFF_STG % 1024 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -96,7 +108,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
            (2ull << 61);
 }
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t IDESC_TF32_M128_N256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -129,6 +140,44 @@ __device__ __forceinline__ float tf32_round(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; the two K-chunks of a row group are
+// LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart (panel operand, K = 8 fp32).
+__device__ __forceinline__ uint64_t umma_desc_panel(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+           (1ull << 46);
+}
+// kind::tf32, fp32 accumulate, K-major A and B, M = N = 128; NEG: A negated (trailing update)
+constexpr uint32_t IDESC_TF32_M128_N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_TF32_M128_N128_NEG = IDESC_TF32_M128_N128 | (1u << 13);
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {  // arrive when this thread's copies have landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void group_bar(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GROUP) : "memory");
+}
+
 }  // namespace tc
 
 using namespace tc;
@@ -140,23 +189,26 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
     float* bvec = reinterpret_cast<float*>(smem + OFF_BVEC);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
     const uint32_t bars = smem_base + OFF_BARS;
-    // barrier ids
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
-    auto bar_acc_full = [&](int b) { return bars + 8u * (2 * NSTAGE + b); };
-    auto bar_acc_empty = [&](int b) { return bars + 8u * (2 * NSTAGE + 2 + b); };
-    auto bar_b_full = [&](int b) { return bars + 8u * (2 * NSTAGE + 4 + b); };
-    auto bar_b_empty = [&](int b) { return bars + 8u * (2 * NSTAGE + 6 + b); };
+    auto bar_stg = [&](int s) { return bars + 8u * (2 * NSTAGE + s); };
+    auto bar_acc_full = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + g); };
+    auto bar_acc_empty = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + NGROUP + g); };
+    auto bar_b_full = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + 2 * NGROUP + g); };
+    auto bar_b_empty = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + 3 * NGROUP + g); };
+    auto bar_panel = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + 4 * NGROUP + g); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), GATHER_THREADS); mbar_init(bar_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_acc_full(b), 1);
-            mbar_init(bar_acc_empty(b), s128::GROUP);
-            mbar_init(bar_b_full(b), GATHER_THREADS);
-            mbar_init(bar_b_empty(b), s128::GROUP);
+        for (int s = 0; s < NSTG; ++s) mbar_init(bar_stg(s), GATHER_THREADS);
+        for (int g = 0; g < NGROUP; ++g) {
+            mbar_init(bar_acc_full(g), 1);
+            mbar_init(bar_acc_empty(g), GROUP);
+            mbar_init(bar_b_full(g), GATHER_THREADS);
+            mbar_init(bar_b_empty(g), GROUP);
+            mbar_init(bar_panel(g), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -174,10 +226,13 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
     const int64_t first = blockIdx.x, step = gridDim.x;
 
     if (warp < 4) {
-        // =============================== GATHER ===============================
-        // Software pipeline over the CTA's flattened (row, chunk) sequence: while chunk c is
-        // scaled/split/stored, the 32 factor loads of chunk c+1 and the index/weight loads of
-        // chunk c+2 are already in flight.
+        // =============================== GATHER + GRAM MMA ISSUE ===============================
+        // Flattened (row, chunk) sequence of this CTA, three chunks deep:
+        //   chunk i+3: index/weight of the entries -> registers (lanes 0-7 of each warp, 8 entries per warp)
+        //   chunk i+2: 32 x 512-B factor rows -> raw staging buffer with cp.async (16 B per lane,
+        //              one coalesced row per warp instruction, no registers held), completion on an mbarrier
+        //   chunk i  : thread m reads column m of the staged rows, scales, splits to TF32 hi/lo, stores the
+        //              K-major swizzled operand tiles; after the gather barrier thread 0 issues the MMAs.
         const int m = tid;  // feature index
         struct Cursor {
             int64_t r, base, hi;  // position in the CTA's row list, first entry of the chunk, row end
@@ -191,104 +246,113 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
             }
         };
         auto advance = [&](Cursor& c) {
+            if (c.r >= rows) return;
             c.base += CHUNK;
             if (c.base >= c.hi) { c.r += step; seek(c); }
         };
-        // raw index/weight of this lane's entry: loaded two chunks ahead, first touched one chunk
-        // later (the in-order pipe would otherwise stall on the load right here)
         struct Raw { int idx; float d; };
-        struct Meta { int64_t off; float sq, dp1; };
         bool saw_negative = false;
-        auto load_raw = [&](const Cursor& c) {
+        auto load_raw = [&](const Cursor& c) {  // lane l < 8 of warp w: entry 8w + l of the chunk
             Raw rw{-1, 0.f};
-            if (c.r < rows) {
-                const int64_t e = c.base + lane;
+            if (c.r < rows && lane < 8) {
+                const int64_t e = c.base + warp * 8 + lane;
                 if (e < c.hi) { rw.d = __ldg(p.data + e); rw.idx = __ldg(p.indices + e); }
             }
             return rw;
         };
-        auto to_meta = [&](const Raw& rw) {
-            Meta mt{0, 0.f, 0.f};
-            if (rw.idx >= 0) {
-                mt.off = (int64_t)rw.idx * p.ldy;
-                if (rw.d < 0.f) saw_negative = true;
-                mt.sq = sqrtf(fabsf(rw.d));
-                mt.dp1 = __fadd_rn(rw.d, 1.0f);
+        float2* metaS = reinterpret_cast<float2*>(smem + OFF_META);
+        auto issue = [&](const Raw& rw, int buf) {
+            if (lane < 8) {
+                float sq = 0.f, dp1 = 0.f;
+                if (rw.idx >= 0) {
+                    if (rw.d < 0.f) saw_negative = true;
+                    sq = sqrtf(fabsf(rw.d));
+                    dp1 = __fadd_rn(rw.d, 1.0f);
+                }
+                metaS[buf * CHUNK + warp * 8 + lane] = make_float2(sq, dp1);
             }
-            return mt;
+            const uint32_t dst0 = smem_base + OFF_STG + buf * STG_BYTES + (warp * 8) * (F * 4) + lane * 16;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int idx = __shfl_sync(0xffffffffu, rw.idx, jj);
+                const float* src = p.Y + (int64_t)(idx >= 0 ? idx : 0) * p.ldy + lane * 4;
+                cp_async16(dst0 + jj * (F * 4), src, idx >= 0 ? 16u : 0u);  // size 0 -> zero fill
+            }
+            cp_async_arrive(bar_stg(buf));
         };
         Cursor c0{first, 0, 0};
         seek(c0);
-        Cursor c1 = c0;
-        if (c1.r < rows) advance(c1);
-        Cursor c2 = c1;
-        if (c2.r < rows) advance(c2);
-        Meta m0 = to_meta(load_raw(c0));
-        Raw r1 = load_raw(c1);
-        float v0[CHUNK];
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) v0[j] = __ldg(p.Y + __shfl_sync(0xffffffffu, m0.off, j) + m);
+        Cursor c1 = c0; advance(c1);
+        Cursor c2 = c1; advance(c2);
+        Cursor c3 = c2; advance(c3);
+        issue(load_raw(c0), 0);
+        issue(load_raw(c1), 1);
+        Raw r2 = load_raw(c2);
         uint32_t chunk_n = 0, row_n = 0;
         double bacc = 0.0;
         const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
-        long long t_empty = 0, t_bempty = 0, t_start = prof ? clock64() : 0, tt = 0;
+        long long t_empty = 0, t_bempty = 0, t_stg = 0, t_acc = 0, t_start = prof ? clock64() : 0, tt = 0;
+        long long t_issue = 0, t_xform = 0, t_bar = 0, t_mma = 0, t2 = 0;
         while (c0.r < rows) {
-            // issue the next chunk's factor loads and the chunk-after-next's index loads
-            const Meta m1 = to_meta(r1);  // loaded one iteration ago
-            float v1[CHUNK];
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) v1[j] = __ldg(p.Y + __shfl_sync(0xffffffffu, m1.off, j) + m);
-            const Raw r2 = load_raw(c2);  // first use: next iteration
-            const int s = chunk_n % NSTAGE;
-            const uint32_t ph = (chunk_n / NSTAGE) & 1u;
-            if (prof) tt = clock64();
-            mbar_wait(bar_empty(s), ph ^ 1u);
-            if (prof) t_empty += clock64() - tt;
+            if (prof) t2 = clock64();
+            // buffer (i+2)%3 was read by every gather thread during iteration i-1: barrier before refilling it
+            asm volatile("bar.sync %0, %1;" ::"n"(1 + NGROUP), "n"(GATHER_THREADS) : "memory");
+            issue(r2, (chunk_n + 2) % NSTG);   // chunk i+2
+            r2 = load_raw(c3);                 // chunk i+3, first touched next iteration
+            const int s = chunk_n % NSTAGE, sb = chunk_n % NSTG;
+            if (prof) { tt = clock64(); t_issue += tt - t2; }
+            mbar_wait(bar_stg(sb), (chunk_n / NSTG) & 1u);
+            if (prof) { t_stg += clock64() - tt; tt = clock64(); }
+            mbar_wait(bar_empty(s), ((chunk_n / NSTAGE) & 1u) ^ 1u);
+            if (prof) { t2 = clock64(); t_empty += t2 - tt; }
+            const float* stg = reinterpret_cast<const float*>(smem + OFF_STG + sb * STG_BYTES) + m;
+            const float2* mt = metaS + sb * CHUNK;
             uint8_t* tile_h = smem + OFF_STAGES + s * STAGE_BYTES + m * 128;
             uint8_t* tile_l = tile_h + TILE_BYTES;
             float part = 0.f;
 #pragma unroll
-            for (int g = 0; g < CHUNK / 4; ++g) {
+            for (int g4 = 0; g4 < CHUNK / 4; ++g4) {
                 float zh[4], zl[4];
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const int j = g * 4 + jj;
-                    const float sj = __shfl_sync(0xffffffffu, m0.sq, j);
-                    const float cj = __shfl_sync(0xffffffffu, m0.dp1, j);
-                    const float z = sj * v0[j];
+                    const int j = g4 * 4 + jj;
+                    const float v = stg[j * F];
+                    const float2 sc = mt[j];
+                    const float z = sc.x * v;
                     zh[jj] = tf32_round(z);
                     zl[jj] = tf32_round(z - zh[jj]);
-                    part = fmaf(cj, v0[j], part);
+                    part = fmaf(sc.y, v, part);
                 }
-                const int sw = (g ^ (m & 7)) << 4;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+                const int sw = (g4 ^ (m & 7)) << 4;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
                 *reinterpret_cast<float4*>(tile_h + sw) = make_float4(zh[0], zh[1], zh[2], zh[3]);
                 *reinterpret_cast<float4*>(tile_l + sw) = make_float4(zl[0], zl[1], zl[2], zl[3]);
             }
             bacc += (double)part;
+            if (prof) { tt = clock64(); t_xform += tt - t2; }
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full(s));
+            if (prof) { t2 = clock64(); t_bar += t2 - tt; }
+            const bool last_chunk = c0.base + CHUNK >= c0.hi;
+            const int g = row_n % NGROUP;
             ++chunk_n;
-            if (c0.base + CHUNK >= c0.hi) {  // last chunk of its row: hand the rhs to the solver group
-                const int b = row_n & 1;
-                const uint32_t bph = (row_n >> 1) & 1u;
+            if (last_chunk) {  // hand the rhs to the solver group that owns this row
+                const uint32_t bph = (row_n / NGROUP) & 1u;
                 if (prof) tt = clock64();
-                mbar_wait(bar_b_empty(b), bph ^ 1u);
+                mbar_wait(bar_b_empty(g), bph ^ 1u);
                 if (prof) t_bempty += clock64() - tt;
-                bvec[b * F + m] = (float)bacc;
-                mbar_arrive(bar_b_full(b));
+                bvec[g * F + m] = (float)bacc;
+                mbar_arrive(bar_b_full(g));
                 bacc = 0.0;
                 ++row_n;
             }
-            c0 = c1; c1 = c2;
-            if (c2.r < rows) advance(c2);
-            m0 = m1; r1 = r2;
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) v0[j] = v1[j];
+            c0 = c1; c1 = c2; c2 = c3;
+            advance(c3);
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         if (saw_negative) atomicOr(flags, 1);
-        if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = chunk_n; p.prof[4] = row_n; }
+        if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = chunk_n; p.prof[4] = row_n; p.prof[5] = t_stg; p.prof[6] = t_acc; p.prof[11] = t_issue; p.prof[12] = t_xform; p.prof[13] = t_bar; p.prof[14] = t_mma; }
     } else if (warp == MMA_WARP) {
-        // =============================== MMA ISSUE ===============================
+        // =============================== GRAM MMA ISSUE ===============================
         if (lane == 0) {
             uint32_t chunk_n = 0, row_n = 0;
             const bool prof = p.prof != nullptr && blockIdx.x == 0;
@@ -297,13 +361,13 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                 const int64_t row = p.row_order ? p.row_order[r] : r;
                 const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
                 if (lo == hi) continue;
-                const int b = row_n & 1;
-                const uint32_t aph = (row_n >> 1) & 1u;
+                const int g = row_n % NGROUP;
+                const uint32_t aph = (row_n / NGROUP) & 1u;
                 if (prof) tt = clock64();
-                mbar_wait(bar_acc_empty(b), aph ^ 1u);
+                mbar_wait(bar_acc_empty(g), aph ^ 1u);
                 if (prof) t_accempty += clock64() - tt;
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(b * 256);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
                 uint32_t accumulate = 0;
                 for (int64_t base = lo; base < hi; base += CHUNK, ++chunk_n) {
                     const int s = chunk_n % NSTAGE;
@@ -315,134 +379,245 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                     const int kc = (int)((hi - base) < CHUNK ? (hi - base) : CHUNK);
                     const int nk = (kc + 7) >> 3;
                     const uint32_t tile = smem_base + OFF_STAGES + s * STAGE_BYTES;
-                    const uint64_t desc = umma_desc(tile);
+                    const uint64_t dh = umma_desc(tile), dl = umma_desc(tile + TILE_BYTES);
                     for (int k = 0; k < nk; ++k) {
                         // advance 8 fp32 = 32 B along K inside the 128-B swizzle row
-                        const uint64_t dk = desc + (uint64_t)(k * 2);
-                        umma_tf32(d_tmem, dk, dk, IDESC_TF32_M128_N256, accumulate);
+                        const uint64_t hk = dh + (uint64_t)(k * 2), lk = dl + (uint64_t)(k * 2);
+                        umma_tf32(d_tmem, hk, hk, IDESC_TF32_M128_N128, accumulate);  // zh zh^T
+                        umma_tf32(d_tmem, hk, lk, IDESC_TF32_M128_N128, 1u);          // zh zl^T
+                        umma_tf32(d_tmem, lk, hk, IDESC_TF32_M128_N128, 1u);          // zl zh^T
                         accumulate = 1;
                     }
                     tc_commit(bar_empty(s));
                 }
-                tc_commit(bar_acc_full(b));
+                tc_commit(bar_acc_full(g));
                 ++row_n;
             }
             if (prof) { p.prof[8] = clock64() - t_start; p.prof[9] = t_full; p.prof[10] = t_accempty; }
         }
     } else {
-        // =============================== SOLVE ===============================
-        // Two groups of 128 threads; group g owns the CTA's non-empty rows with (row_n & 1) == g,
-        // which is also the accumulator buffer it drains.
-        const int g = (warp - 5) >> 2;
-        const int q = warp & 3;        // TMEM lane quarter this warp may read
-        const int i = q * 32 + lane;   // matrix row owned by this thread (0..127)
-        float* A = reinterpret_cast<float*>(smem + OFF_A + g * A_BYTES);
-        float* LpT = reinterpret_cast<float*>(smem + OFF_LPT + g * LPT_BYTES);
-        float* dinv = reinterpret_cast<float*>(smem + OFF_DINV + g * F * 4);
-        float* xs = reinterpret_cast<float*>(smem + OFF_XS + g * F * 4);
-        constexpr int LDA = s128::LDA;
-        auto gsync = [&]() {
-            if (g == 0) s128::group_sync<1>(); else s128::group_sync<2>();
-        };
-        uint32_t row_n = 0;
-        const bool prof = p.prof != nullptr && blockIdx.x == 0 && g == 0 && i == 0;
-        long long t_accfull = 0, t_drain = 0, t_g = 0, t_bfull = 0, t_solve = 0, t_start = prof ? clock64() : 0, tt = 0;
+        // =============================== SOLVE (matrix resident in TMEM) ===============================
+        const int g = (warp - SOLVER_WARP0) >> 2;
+        const int q = warp & 3;        // TMEM lane quarter this warp may access
+        const int t = q * 32 + lane;   // matrix row owned by this thread = TMEM lane
+        const int bar_id = 1 + g;
+        uint8_t* gs = smem + OFF_GROUPS + g * GROUP_BYTES;
+        uint8_t* tileH = gs + G_OFF_TILEH;
+        uint8_t* tileL = gs + G_OFF_TILEL;
+        float* Dblk = reinterpret_cast<float*>(gs + G_OFF_DBLK);
+        float* bblk = reinterpret_cast<float*>(gs + G_OFF_BBLK);
+        float* red = reinterpret_cast<float*>(gs + G_OFF_RED);
+        float* dinv = reinterpret_cast<float*>(gs + G_OFF_DINV);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * F);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
+        const uint64_t descH = umma_desc_panel(smem_u32(tileH)), descL = umma_desc_panel(smem_u32(tileL));
+        const float* Grow = p.G + t * F;
+        uint32_t row_n = 0, my_rows = 0, panel_n = 0;
+        const bool prof = p.prof != nullptr && blockIdx.x == 0 && g == 0 && t == 0;
+        long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
         for (int64_t r = first; r < rows; r += step) {
             const int64_t row = p.row_order ? p.row_order[r] : r;
             const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
             float* xout = p.X + row * p.ldx;
             if (lo == hi) {  // wmf_model.py:223-225
-                if (g == 0) xout[i] = 0.0f;
+                if (g == 0) xout[t] = 0.0f;
                 continue;
             }
-            const int b = row_n & 1;
-            const uint32_t ph = (row_n >> 1) & 1u;
+            const bool mine = (int)(row_n % NGROUP) == g;
             ++row_n;
-            if (b != g) continue;
+            if (!mine) continue;
+            const uint32_t ph = my_rows & 1u;
+            ++my_rows;
             if (prof) tt = clock64();
-            mbar_wait(bar_acc_full(b), ph);
-            if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
+            mbar_wait(bar_b_full(g), ph);
+            float bt = bvec[g * F + t];
+            mbar_arrive(bar_b_empty(g));
+            mbar_wait(bar_acc_full(g), ph);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
-            // phase 1: own row: A[i][j] = P[i][j] + Q[i][j] (j < i), P + 2Q on the diagonal
+            if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
+            bool ok = true;
+            // ------------------------------ factorisation, 16 panels ------------------------------
 #pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-                const int col0 = cb * 32;
-                if (col0 > i) break;  // nothing at or left of the diagonal in this block (warp-uniform: i>>5)
-                float pv[32], qv[32];
-                tmem_ld32(t_row + col0, pv);
-                tmem_ld32(t_row + 128 + col0, qv);
+            for (int c0 = 0; c0 < F; c0 += NB) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(Grow + c0));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(Grow + c0 + 4));
+                if (c0 > 0) {  // trailing update of the previous panel has landed in TMEM
+                    mbar_wait(bar_panel(g), panel_n & 1u);
+                    ++panel_n;
+                    tc_fence_after();
+                }
+                float a[NB];
+                tmem_ld8(t_row + c0, a);
+                a[0] = __fadd_rn(a[0], g0.x); a[1] = __fadd_rn(a[1], g0.y); a[2] = __fadd_rn(a[2], g0.z);
+                a[3] = __fadd_rn(a[3], g0.w); a[4] = __fadd_rn(a[4], g1.x); a[5] = __fadd_rn(a[5], g1.y);
+                a[6] = __fadd_rn(a[6], g1.z); a[7] = __fadd_rn(a[7], g1.w);
+                const int rel = t - c0;
+                if (rel >= 0 && rel < NB) {
+                    *reinterpret_cast<float4*>(Dblk + rel * NB) = make_float4(a[0], a[1], a[2], a[3]);
+                    *reinterpret_cast<float4*>(Dblk + rel * NB + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                    bblk[rel] = bt;
+                }
+                group_bar(bar_id);
+                // 8x8 diagonal block: factored redundantly by every thread (no communication in the chain)
+                float L[NB][NB], rinv[NB], zb[NB];
+                {
+                    float D[NB][NB];
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int j0 = col0 + c4 * 4;
-                    if (j0 <= i) {
-                        float o[4];
+                    for (int rr = 0; rr < NB; ++rr) {
+                        const float4 d0 = *reinterpret_cast<const float4*>(Dblk + rr * NB);
+                        const float4 d1 = *reinterpret_cast<const float4*>(Dblk + rr * NB + 4);
+                        D[rr][0] = d0.x; D[rr][1] = d0.y; D[rr][2] = d0.z; D[rr][3] = d0.w;
+                        D[rr][4] = d1.x; D[rr][5] = d1.y; D[rr][6] = d1.z; D[rr][7] = d1.w;
+                    }
+                    const float4 b0 = *reinterpret_cast<const float4*>(bblk);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bblk + 4);
+                    const float bb[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float qq = qv[c4 * 4 + e];
-                            o[e] = pv[c4 * 4 + e] + qq + ((j0 + e == i) ? qq : 0.0f);
+                    for (int j = 0; j < NB; ++j) {
+                        float sd = D[j][j];
+#pragma unroll
+                        for (int k = 0; k < j; ++k) sd = fmaf(-L[j][k], L[j][k], sd);
+                        ok = ok && (sd > 0.0f);
+                        float ri = rsqrtf(sd);
+                        ri = ri * fmaf(-0.5f * sd, ri * ri, 1.5f);  // one Newton step: ~1 ulp
+                        rinv[j] = ri;
+                        L[j][j] = sd * ri;
+#pragma unroll
+                        for (int i = j + 1; i < NB; ++i) {
+                            float v = D[i][j];
+#pragma unroll
+                            for (int k = 0; k < j; ++k) v = fmaf(-L[i][k], L[j][k], v);
+                            L[i][j] = v * ri;
                         }
-                        *reinterpret_cast<float4*>(A + i * LDA + j0) = make_float4(o[0], o[1], o[2], o[3]);
+                        float zz = bb[j];  // forward substitution of the block's rhs
+#pragma unroll
+                        for (int k = 0; k < j; ++k) zz = fmaf(-L[j][k], zb[k], zz);
+                        zb[j] = zz * ri;
                     }
                 }
-            }
-            gsync();
-            // phase 2: transposed part: A[j][i] += Q[i][j] (j > i); exactly one writer per element
-#pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-                const int col0 = cb * 32;
-                if (col0 + 31 <= (i & ~31)) continue;  // whole block at or left of this warp's rows (warp-uniform)
-                float qv[32];
-                tmem_ld32(t_row + 128 + col0, qv);
+                // own row against the block
+                float l[NB];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int j = col0 + c;
-                    if (j > i) A[j * LDA + i] += qv[c];
+                for (int j = 0; j < NB; ++j) {
+                    float v = a[j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) v = fmaf(-l[k], L[j][k], v);
+                    v *= rinv[j];
+                    l[j] = (rel < 0 || j > rel) ? 0.0f : v;  // dead rows; nothing right of the diagonal
                 }
+                if (rel >= NB) {
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) bt = fmaf(-l[k], zb[k], bt);
+                } else if (rel >= 0) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                        if (rel == j) bt = zb[j];  // z of this row is final
+                }
+                if (rel == 0) {
+                    *reinterpret_cast<float4*>(dinv + c0) = make_float4(rinv[0], rinv[1], rinv[2], rinv[3]);
+                    *reinterpret_cast<float4*>(dinv + c0 + 4) = make_float4(rinv[4], rinv[5], rinv[6], rinv[7]);
+                }
+                tmem_st8(t_row + c0, l);  // finished L over the dead columns (back substitution reads it)
+                if (c0 + NB < F) {
+                    float lh[NB], ll[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const float v = rel >= NB ? l[j] : 0.0f;  // only rows below the block take part
+                        lh[j] = tf32_round(v);
+                        ll[j] = tf32_round(v - lh[j]);
+                    }
+                    const int o = (t >> 3) * 256 + (t & 7) * 16;
+                    *reinterpret_cast<float4*>(tileH + o) = make_float4(lh[0], lh[1], lh[2], lh[3]);
+                    *reinterpret_cast<float4*>(tileH + o + 128) = make_float4(lh[4], lh[5], lh[6], lh[7]);
+                    *reinterpret_cast<float4*>(tileL + o) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+                    *reinterpret_cast<float4*>(tileL + o + 128) = make_float4(ll[4], ll[5], ll[6], ll[7]);
+                    fence_async_smem();
+                }
+                tc_fence_before();
+                group_bar(bar_id);
+                if (c0 + NB < F && t == 0) {  // S -= L L^T on the whole accumulator (dead rows/columns are zero)
+                    tc_fence_after();
+                    umma_tf32(d_tmem, descH, descH, IDESC_TF32_M128_N128_NEG, 1u);
+                    umma_tf32(d_tmem, descH, descL, IDESC_TF32_M128_N128_NEG, 1u);
+                    umma_tf32(d_tmem, descL, descH, IDESC_TF32_M128_N128_NEG, 1u);
+                    tc_commit(bar_panel(g));
+                }
+            }
+            if (prof) { t_fact += clock64() - tt; tt = clock64(); }
+            // ------------------------------ back substitution  L^T x = z ------------------------------
+            // Row-oriented: x_t = (z_t - sum_{i>t} L[i][t] x_i) / L[t][t]. Thread i re-reads its own 8 panel
+            // values from its TMEM lane, contributes L[i][c0+j] * x_i, and the 8 sums are reduced over the
+            // group (shuffle tree + 4 partials in shared memory, fixed order). One barrier per block.
+            float xt = 0.0f;
+#pragma unroll 1
+            for (int c0 = F - NB; c0 >= 0; c0 -= NB) {
+                const int par = (c0 >> 3) & 1;
+                float l[NB];
+                tmem_ld8(t_row + c0, l);
+                const int rel = t - c0;
+                float cj[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) cj[j] = rel >= NB ? l[j] * xt : 0.0f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) cj[j] += __shfl_xor_sync(0xffffffffu, cj[j], o);
+                if (lane == 0) {
+                    *reinterpret_cast<float4*>(red + (par * 4 + q) * NB) = make_float4(cj[0], cj[1], cj[2], cj[3]);
+                    *reinterpret_cast<float4*>(red + (par * 4 + q) * NB + 4) = make_float4(cj[4], cj[5], cj[6], cj[7]);
+                }
+                if (rel >= 0 && rel < NB) {
+                    *reinterpret_cast<float4*>(Dblk + par * 64 + rel * NB) = make_float4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<float4*>(Dblk + par * 64 + rel * NB + 4) = make_float4(l[4], l[5], l[6], l[7]);
+                    bblk[par * NB + rel] = bt;
+                }
+                group_bar(bar_id);
+                float x[NB];
+                {
+                    float sj[NB];
+                    {
+                        const float4 z0 = *reinterpret_cast<const float4*>(bblk + par * NB);
+                        const float4 z1 = *reinterpret_cast<const float4*>(bblk + par * NB + 4);
+                        sj[0] = z0.x; sj[1] = z0.y; sj[2] = z0.z; sj[3] = z0.w;
+                        sj[4] = z1.x; sj[5] = z1.y; sj[6] = z1.z; sj[7] = z1.w;
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const float4 p0 = *reinterpret_cast<const float4*>(red + (par * 4 + w) * NB);
+                        const float4 p1 = *reinterpret_cast<const float4*>(red + (par * 4 + w) * NB + 4);
+                        sj[0] -= p0.x; sj[1] -= p0.y; sj[2] -= p0.z; sj[3] -= p0.w;
+                        sj[4] -= p1.x; sj[5] -= p1.y; sj[6] -= p1.z; sj[7] -= p1.w;
+                    }
+                    const float4 r0 = *reinterpret_cast<const float4*>(dinv + c0);
+                    const float4 r1 = *reinterpret_cast<const float4*>(dinv + c0 + 4);
+                    const float ri[NB] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    float Lb[NB][NB];
+#pragma unroll
+                    for (int rr = 0; rr < NB; ++rr) {
+                        const float4 d0 = *reinterpret_cast<const float4*>(Dblk + par * 64 + rr * NB);
+                        const float4 d1 = *reinterpret_cast<const float4*>(Dblk + par * 64 + rr * NB + 4);
+                        Lb[rr][0] = d0.x; Lb[rr][1] = d0.y; Lb[rr][2] = d0.z; Lb[rr][3] = d0.w;
+                        Lb[rr][4] = d1.x; Lb[rr][5] = d1.y; Lb[rr][6] = d1.z; Lb[rr][7] = d1.w;
+                    }
+#pragma unroll
+                    for (int j = NB - 1; j >= 0; --j) {
+                        float v = sj[j];
+#pragma unroll
+                        for (int rr = j + 1; rr < NB; ++rr) v = fmaf(-Lb[rr][j], x[rr], v);
+                        x[j] = v * ri[j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if (rel == j) xt = x[j];
             }
             tc_fence_before();
-            mbar_arrive(bar_acc_empty(b));  // the tensor core may start the row after next
-            gsync();
-            if (prof) { t_drain += clock64() - tt; tt = clock64(); }
-            // + G once (wmf_model.py:239 adds YTY_I to the finished weighted Gram), rhs into row 128
-            // (batches of 8 independent 16-byte loads: G lives in L2, one exposed latency per batch)
-#pragma unroll 1
-            for (int e0 = i; e0 < F * (F / 4); e0 += s128::GROUP * 8) {
-                float4 gv[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e4 = e0 + u * s128::GROUP;
-                    const int rr = e4 >> 5, c4 = (e4 & 31) * 4;
-                    gv[u] = (c4 <= rr) ? __ldg(reinterpret_cast<const float4*>(p.G + rr * F + c4)) : make_float4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int e4 = e0 + u * s128::GROUP;
-                    const int rr = e4 >> 5, c4 = (e4 & 31) * 4;
-                    if (c4 <= rr) {
-                        float4* dst = reinterpret_cast<float4*>(A + rr * LDA + c4);
-                        float4 v = *dst;
-                        v.x = __fadd_rn(v.x, gv[u].x); v.y = __fadd_rn(v.y, gv[u].y);
-                        v.z = __fadd_rn(v.z, gv[u].z); v.w = __fadd_rn(v.w, gv[u].w);
-                        *dst = v;
-                    }
-                }
-            }
-            if (prof) { t_g += clock64() - tt; tt = clock64(); }
-            mbar_wait(bar_b_full(b), ph);
-            if (prof) { t_bfull += clock64() - tt; tt = clock64(); }
-            A[F * LDA + i] = bvec[b * F + i];
-            mbar_arrive(bar_b_empty(b));
-            gsync();
-            bool ok;
-            if (g == 0) ok = s128::chol_solve_128<1>(A, LpT, dinv, xs, i);
-            else ok = s128::chol_solve_128<2>(A, LpT, dinv, xs, i);
-            if (ok) xout[i] = xs[i];
-            else if (i == 0) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
-            gsync();
-            if (prof) t_solve += clock64() - tt;
+            mbar_arrive(bar_acc_empty(g));  // accumulator g is free for the Gram of this group's next row
+            if (ok) xout[t] = xt;
+            else if (t == 0) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
+            if (prof) t_back += clock64() - tt;
         }
-        if (prof) { p.prof[16] = clock64() - t_start; p.prof[17] = t_accfull; p.prof[18] = t_drain; p.prof[19] = t_g; p.prof[20] = t_bfull; p.prof[21] = t_solve; p.prof[22] = row_n; }
+        if (prof) { p.prof[16] = clock64() - t_start; p.prof[17] = t_accfull; p.prof[18] = t_fact; p.prof[19] = t_back; p.prof[22] = my_rows; }
     }
     // =============================== TEARDOWN ===============================
     tc_fence_before();

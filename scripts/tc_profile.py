@@ -18,12 +18,14 @@ def run(csr, Yd, name):
         e0.record(); X = engine.half_step(csr, Yd, G, algo=_lib.ALGO_TCGEN05); e1.record(); torch.cuda.synchronize()
     ws = engine.workspace(0, dev)
     prof = ws[64:256].view(torch.int64).cpu().numpy()
+    flags = ws[0:8].view(torch.int32).cpu().numpy()
     ms = e0.elapsed_time(e1)
-    print(f"{name}: {ms:.2f} ms")
+    print(f"{name}: {ms:.2f} ms  flags={flags}")
     f = lambda c: f"{c/1.965e6:.2f}ms"
-    print("  gather total", f(prof[0]), "wait_empty", f(prof[1]), "wait_bempty", f(prof[2]), "chunks", prof[3], "rows", prof[4])
+    print("  gather total", f(prof[0]), "wait_empty", f(prof[1]), "wait_bempty", f(prof[2]), "wait_stg", f(prof[5]), "wait_accempty(t0)", f(prof[6]), "chunks", prof[3], "rows", prof[4])
+    print("  gather phases: issue", f(prof[11]), "transform", f(prof[12]), "fence+bar", f(prof[13]), "-", f(prof[14]))
     print("  mma total", f(prof[8]), "wait_full", f(prof[9]), "wait_accempty", f(prof[10]))
-    print("  solver0 total", f(prof[16]), "wait_accfull", f(prof[17]), "drain", f(prof[18]), "G", f(prof[19]), "wait_bfull", f(prof[20]), "solve", f(prof[21]), "rows", prof[22])
+    print("  solver0 total", f(prof[16]), "wait(b,acc)full", f(prof[17]), "factor", f(prof[18]), "backsub", f(prof[19]), "rows", prof[22])
     return X
 U = run(Cd, Y, "user half-step")
 run(CT, U, "item half-step")
