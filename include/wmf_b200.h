@@ -67,14 +67,18 @@ int wmf_gram(const float* Y, int64_t n, int f, int64_t ldy, float lambda, int on
  *   x_r = (G + sum_j d_j y_j y_j^T)^-1  sum_j (d_j+1) y_j ,   j over the stored entries of row r
  * bias != 0: y_j has column 0 replaced by 1 and d_j = data_j - Y[j*ldy+0] (:328-343); G must
  * then come from wmf_gram(..., ones_col0=1). Rows with no entries give the zero vector
- * (:223-225; with bias solve(G,0)=0 is the same). `row_order` (nullable) is a permutation of
- * [0,rows) giving the processing order (longest rows first balances the power-law tail); it
- * does not change any row's arithmetic. X row r is written at X + r*ldx. */
+ * (:223-225; with bias solve(G,0)=0 is the same). `row_order` (nullable) is the processing
+ * schedule: int32[order_len] holding every row id of [0,rows) exactly once plus any number of
+ * -1 padding slots. The persistent CTAs deal its entries out round-robin (slot s goes to CTA
+ * s mod gridDim on the tcgen05 path, to the next free CTA on the SIMT path), so a schedule
+ * built with longest rows first and heavy rows paired with light ones balances the power-law
+ * tail; it never changes a row's arithmetic. X row r is written at X + r*ldx. */
 size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo);
 /* 1 if `algo` (WMF_ALGO_SIMT / WMF_ALGO_TCGEN05) handles factor width f with/without bias, else 0. */
 int wmf_als_half_step_supports(int algo, int f, int bias);
 int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data,
-                      int64_t rows, const int32_t* row_order, const float* Y, int64_t ldy, int f,
+                      int64_t rows, const int32_t* row_order, int64_t order_len, const float* Y,
+                      int64_t ldy, int f,
                       const float* G, int bias, float* X, int64_t ldx, int algo, void* ws,
                       size_t ws_bytes, void* stream);
 

@@ -10,6 +10,7 @@ struct HalfStepParams {
     const float* data;
     int64_t rows;
     const int32_t* row_order;
+    int64_t sched_len;  // schedule slots to walk: order_len, or rows without a schedule
     const float* Y;
     int64_t ldy;
     int f;

@@ -31,7 +31,8 @@ size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo) {
 }
 
 int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows,
-                      const int32_t* row_order, const float* Y, int64_t ldy, int f, const float* G, int bias,
+                      const int32_t* row_order, int64_t order_len, const float* Y, int64_t ldy, int f,
+                      const float* G, int bias,
                       float* X, int64_t ldx, int algo, void* ws, size_t ws_bytes, void* stream) {
     WMF_REQUIRE(f > 0 && f <= WMF_MAX_F && (!bias || f >= 2), "wmf_als_half_step: f=%d outside 1..%d", f, WMF_MAX_F);
     WMF_REQUIRE(rows >= 0 && rows < (1ll << 31), "wmf_als_half_step: rows=%lld out of range", (long long)rows);
@@ -41,7 +42,9 @@ int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float
                 "wmf_als_half_step: unknown algo %d", algo);
     const int chosen = resolve_algo(algo, f, bias);
     HalfStepParams p{};
+    WMF_REQUIRE(row_order == nullptr || order_len >= rows, "wmf_als_half_step: schedule shorter than rows");
     p.indptr = indptr; p.indices = indices; p.data = data; p.rows = rows; p.row_order = row_order;
+    p.sched_len = row_order ? order_len : rows;
     p.Y = Y; p.ldy = ldy; p.f = f; p.G = G; p.bias = bias; p.X = X; p.ldx = ldx;
     if (chosen == WMF_ALGO_TCGEN05) {
         if (!tc_half_step_supported(f, bias)) {

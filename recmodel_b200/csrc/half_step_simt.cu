@@ -46,8 +46,9 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
         __syncthreads();
         const int64_t r = misc[0];
         __syncthreads();
-        if (r >= p.rows) break;
+        if (r >= p.sched_len) break;
         const int64_t row = p.row_order ? p.row_order[r] : r;
+        if (row < 0) continue;  // padding slot of a balanced schedule
         const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
         float* xout = p.X + row * p.ldx;
         if (lo == hi) {  // wmf_model.py:223-225

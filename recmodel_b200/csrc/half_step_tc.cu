@@ -48,7 +48,7 @@ constexpr int NB = 8;                // Cholesky panel width
 constexpr int NGROUP = 4;            // solver groups = TMEM accumulators
 constexpr int GROUP = 128;
 constexpr int GATHER_THREADS = 128;
-constexpr int SOLVER_WARP0 = 4, MMA_WARP = SOLVER_WARP0 + NGROUP * 4;
+constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WARP0 + 4;  // high warp ids issue first
 constexpr int THREADS = (MMA_WARP + 1) * 32;               // 672
 constexpr uint32_t TMEM_COLS = 512;
 static_assert(NGROUP * F <= 512, "TMEM columns");
@@ -222,10 +222,10 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int64_t rows = p.rows;
+    const int64_t rows = p.sched_len;  // schedule slots; slot s belongs to CTA s % gridDim
     const int64_t first = blockIdx.x, step = gridDim.x;
 
-    if (warp < 4) {
+    if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
         // =============================== GATHER + GRAM MMA ISSUE ===============================
         // Flattened (row, chunk) sequence of this CTA, three chunks deep:
         //   chunk i+3: index/weight of the entries -> registers (lanes 0-7 of each warp, 8 entries per warp)
@@ -233,15 +233,18 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         //              one coalesced row per warp instruction, no registers held), completion on an mbarrier
         //   chunk i  : thread m reads column m of the staged rows, scales, splits to TF32 hi/lo, stores the
         //              K-major swizzled operand tiles; after the gather barrier thread 0 issues the MMAs.
-        const int m = tid;  // feature index
+        const int m = tid - GATHER_WARP0 * 32;  // feature index
+        const int gw = warp - GATHER_WARP0;     // gather warp 0..3
         struct Cursor {
             int64_t r, base, hi;  // position in the CTA's row list, first entry of the chunk, row end
         };
         auto seek = [&](Cursor& c) {  // move c.r forward to the next non-empty row (or past the end)
             while (c.r < rows) {
                 const int64_t row = p.row_order ? p.row_order[c.r] : c.r;
-                const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-                if (lo != hi) { c.base = lo; c.hi = hi; return; }
+                if (row >= 0) {  // -1 = padding slot of the balanced schedule
+                    const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
+                    if (lo != hi) { c.base = lo; c.hi = hi; return; }
+                }
                 c.r += step;
             }
         };
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         auto load_raw = [&](const Cursor& c) {  // lane l < 8 of warp w: entry 8w + l of the chunk
             Raw rw{-1, 0.f};
             if (c.r < rows && lane < 8) {
-                const int64_t e = c.base + warp * 8 + lane;
+                const int64_t e = c.base + gw * 8 + lane;
                 if (e < c.hi) { rw.d = __ldg(p.data + e); rw.idx = __ldg(p.indices + e); }
             }
             return rw;
@@ -269,9 +272,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                     sq = sqrtf(fabsf(rw.d));
                     dp1 = __fadd_rn(rw.d, 1.0f);
                 }
-                metaS[buf * CHUNK + warp * 8 + lane] = make_float2(sq, dp1);
+                metaS[buf * CHUNK + gw * 8 + lane] = make_float2(sq, dp1);
             }
-            const uint32_t dst0 = smem_base + OFF_STG + buf * STG_BYTES + (warp * 8) * (F * 4) + lane * 16;
+            const uint32_t dst0 = smem_base + OFF_STG + buf * STG_BYTES + (gw * 8) * (F * 4) + lane * 16;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const int idx = __shfl_sync(0xffffffffu, rw.idx, jj);
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         Raw r2 = load_raw(c2);
         uint32_t chunk_n = 0, row_n = 0;
         double bacc = 0.0;
-        const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        const bool prof = p.prof != nullptr && blockIdx.x == 0 && m == 0;
         long long t_empty = 0, t_bempty = 0, t_stg = 0, t_acc = 0, t_start = prof ? clock64() : 0, tt = 0;
         long long t_issue = 0, t_xform = 0, t_bar = 0, t_mma = 0, t2 = 0;
         while (c0.r < rows) {
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
             long long t_full = 0, t_accempty = 0, t_start = prof ? clock64() : 0, tt = 0;
             for (int64_t r = first; r < rows; r += step) {
                 const int64_t row = p.row_order ? p.row_order[r] : r;
+                if (row < 0) continue;
                 const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
                 if (lo == hi) continue;
                 const int g = row_n % NGROUP;
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
         for (int64_t r = first; r < rows; r += step) {
             const int64_t row = p.row_order ? p.row_order[r] : r;
+            if (row < 0) continue;
             const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
             float* xout = p.X + row * p.ldx;
             if (lo == hi) {  // wmf_model.py:223-225

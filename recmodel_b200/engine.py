@@ -71,9 +71,12 @@ class DeviceCSR:
 
     @property
     def row_order(self):
+        """Processing schedule for the half-step kernels (see include/wmf_b200.h): rows sorted
+        longest first and dealt to the persistent CTAs in rounds, each round giving its
+        heaviest row to the currently lightest CTA. int32, -1 = padding slot."""
         if self._row_order is None:
-            counts = self.indptr[1:] - self.indptr[:-1]
-            self._row_order = torch.sort(counts, descending=True, stable=True).indices.to(torch.int32)
+            counts = (self.indptr[1:] - self.indptr[:-1]).cpu().numpy()
+            self._row_order = torch.from_numpy(balanced_schedule(counts, _lib.require_device())).to(self.device)
         return self._row_order
 
     def with_data(self, data):
@@ -108,6 +111,53 @@ class DeviceCSR:
         import scipy.sparse
         return scipy.sparse.csr_matrix((self.data.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
                                        shape=self.shape)
+
+
+def balanced_schedule(counts, n_cta, chunk=32, row_overhead=4):
+    """Longest-processing-time schedule for the persistent CTAs. Cost of a row = its 32-entry
+    chunks plus a fixed solve overhead. Returns int32[n_slots * n_cta]; slot k*n_cta + c is
+    the k-th row of CTA c, -1 where that CTA has no k-th row (a CTA that owns a very long row
+    takes fewer rows)."""
+    import heapq
+    counts = np.asarray(counts, dtype=np.int64)
+    rows = len(counts)
+    order = np.argsort(-counts, kind="stable")
+    cost = np.where(counts > 0, (counts + chunk - 1) // chunk + row_overhead, 0).astype(np.int64)[order]
+    if rows == 0:
+        return np.full(n_cta, -1, dtype=np.int32)
+    mean_load = cost.sum() / n_cta
+    if cost[0] < 0.02 * mean_load:  # no heavy head: round-robin over the sorted rows is balanced
+        sched = np.full(((rows + n_cta - 1) // n_cta) * n_cta, -1, dtype=np.int32)
+        sched[:rows] = order
+        return sched
+    # heavy head: greedy LPT for the rows that matter, round-robin over the lightest CTAs for the tail
+    n_head = int(np.searchsorted(-cost, -max(1, int(0.002 * mean_load)), side="right"))
+    lists = [[] for _ in range(n_cta)]
+    heap = [(0, c) for c in range(n_cta)]
+    for k in range(n_head):
+        load, c = heapq.heappop(heap)
+        lists[c].append(order[k])
+        heapq.heappush(heap, (load + int(cost[k]), c))
+    load = np.zeros(n_cta)
+    for l, c in heap:
+        load[c] = l
+    k = n_head
+    while k < rows:  # tail rows are tiny: hand them out in rounds to the currently lightest CTAs
+        take = min(n_cta, rows - k)
+        target = (load.sum() + cost[k:].sum()) / n_cta
+        ctas = np.argsort(load, kind="stable")
+        ctas = ctas[load[ctas] < target][:take]
+        if len(ctas) == 0:
+            ctas = np.argsort(load, kind="stable")[:take]
+        for j, c in enumerate(ctas):
+            lists[c].append(order[k + j])
+        load[ctas] += cost[k:k + len(ctas)]
+        k += len(ctas)
+    n_slots = max(len(l) for l in lists)
+    sched = np.full((n_slots, n_cta), -1, dtype=np.int32)
+    for c, l in enumerate(lists):
+        sched[:len(l), c] = l
+    return sched.reshape(-1)
 
 
 def preprocess_(data, mode, alpha, beta):
@@ -148,8 +198,8 @@ def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_orde
     need = lib.wmf_als_half_step_workspace_bytes(rows, f, algo)
     ws = workspace(need, Y.device)
     order = csr.row_order if use_row_order else None
-    _lib.check(lib.wmf_als_half_step(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), rows, _ptr(order), _ptr(Y),
-                                     Y.stride(0), f, _ptr(G), int(bool(bias)), _ptr(X), X.stride(0), int(algo),
+    _lib.check(lib.wmf_als_half_step(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), rows, _ptr(order),
+                                     0 if order is None else order.numel(), _ptr(Y), Y.stride(0), f, _ptr(G), int(bool(bias)), _ptr(X), X.stride(0), int(algo),
                                      _ptr(ws), ws.numel(), _stream()), "wmf_als_half_step")
     return X
 
