@@ -22,10 +22,11 @@ def run(csr, Yd, name):
     ms = e0.elapsed_time(e1)
     print(f"{name}: {ms:.2f} ms  flags={flags}")
     f = lambda c: f"{c/1.965e6:.2f}ms"
-    print("  gather total", f(prof[0]), "wait_empty", f(prof[1]), "wait_bempty", f(prof[2]), "wait_stg", f(prof[5]), "wait_accempty(t0)", f(prof[6]), "chunks", prof[3], "rows", prof[4])
-    print("  gather phases: issue", f(prof[11]), "transform", f(prof[12]), "fence+bar", f(prof[13]), "-", f(prof[14]))
+    print("  gather total", f(prof[0]), "wait_empty", f(prof[1]), "wait_bempty", f(prof[2]), "chunks", prof[3], "rows", prof[4])
     print("  mma total", f(prof[8]), "wait_full", f(prof[9]), "wait_accempty", f(prof[10]))
     print("  solver0 total", f(prof[16]), "wait(b,acc)full", f(prof[17]), "factor", f(prof[18]), "backsub", f(prof[19]), "rows", prof[22])
+    print("  factor phases: wait_mma", f(prof[7]), "tmem_ld", f(prof[15]), "bar1", f(prof[20]), "chol+trsm", f(prof[21]), "st+split", f(prof[23]), "bar2", f(prof[11]), "mma_issue", f(prof[12]))
+    print("  backsub phases: tmem_ld", f(prof[13]), "reduce", f(prof[14]), "bar", f(prof[5]), "solve", f(prof[6]))
     return X
 U = run(Cd, Y, "user half-step")
 run(CT, U, "item half-step")
