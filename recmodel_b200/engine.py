@@ -126,12 +126,12 @@ def balanced_schedule(counts, n_cta, chunk=32, row_overhead=4):
     if rows == 0:
         return np.full(n_cta, -1, dtype=np.int32)
     mean_load = cost.sum() / n_cta
-    if cost[0] < 0.02 * mean_load:  # no heavy head: round-robin over the sorted rows is balanced
+    if cost[0] < 0.05 * mean_load:  # no heavy head: round-robin over the sorted rows is balanced
         sched = np.full(((rows + n_cta - 1) // n_cta) * n_cta, -1, dtype=np.int32)
         sched[:rows] = order
         return sched
     # heavy head: greedy LPT for the rows that matter, round-robin over the lightest CTAs for the tail
-    n_head = int(np.searchsorted(-cost, -max(1, int(0.002 * mean_load)), side="right"))
+    n_head = int(np.searchsorted(-cost, -max(1, int(0.01 * mean_load)), side="right"))
     lists = [[] for _ in range(n_cta)]
     heap = [(0, c) for c in range(n_cta)]
     for k in range(n_head):
