@@ -32,6 +32,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "half_step.cuh"
+#include "factor8.cuh"
 
 namespace wmf {
 
@@ -57,11 +58,11 @@ static_assert(NGROUP * F <= 512, "TMEM columns");
 constexpr int PANEL_TILE_BYTES = F * NB * 4;          // 4 KB: 128 rows x 8 fp32, K-major, no swizzle
 constexpr int G_OFF_TILEH = 0;
 constexpr int G_OFF_TILEL = G_OFF_TILEH + PANEL_TILE_BYTES;
-constexpr int G_OFF_DBLK = G_OFF_TILEL + PANEL_TILE_BYTES;          // 2 x (8 x 8) floats
-constexpr int G_OFF_BBLK = G_OFF_DBLK + 2 * NB * NB * 4;            // 2 x 8 floats (rhs / z of the block)
-constexpr int G_OFF_RED = G_OFF_BBLK + 2 * NB * 4;                  // 2 x 4 warps x 8 floats
-constexpr int G_OFF_DINV = G_OFF_RED + 2 * 4 * NB * 4;              // 128 floats
-constexpr int GROUP_BYTES = ((G_OFF_DINV + F * 4 + 127) / 128) * 128;
+constexpr int G_OFF_NINV = G_OFF_TILEL + PANEL_TILE_BYTES;          // 16 blocks x (8 x 8) floats: N = L^-1 per pivot block
+constexpr int G_OFF_ZB = G_OFF_NINV + (F / NB) * NB * NB * 4;       // 16 x 8 floats: N b_blk
+constexpr int G_OFF_DBLK = G_OFF_ZB + (F / NB) * NB * 4;            // 8 x 8 pivot block + 8 rhs
+constexpr int G_OFF_BFIN = G_OFF_DBLK + (NB * NB + 2 * NB) * 4;     // 128 floats: final rhs
+constexpr int GROUP_BYTES = ((G_OFF_BFIN + F * 4 + 127) / 128) * 128;
 
 // shared memory carve-up (bytes from a 1024-aligned base)
 constexpr int OFF_STAGES = 0;
@@ -149,7 +150,8 @@ __device__ __forceinline__ uint64_t umma_desc_panel(uint32_t smem_addr) {
 }
 // kind::tf32, fp32 accumulate, K-major A and B, M = N = 128; NEG: A negated (trailing update)
 constexpr uint32_t IDESC_TF32_M128_N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t IDESC_TF32_M128_N128_NEG = IDESC_TF32_M128_N128 | (1u << 13);
+constexpr uint32_t IDESC_TF32_NEG_M128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((128u >> 4) << 24);  // N filled in at issue
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -174,6 +176,32 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {  // arrive when this thread's copies have landed
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// explicit shared-space accesses (generic ld/st on pointers derived from the aligned base cost an
+// address-space check per access)
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts2(uint32_t a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts1(uint32_t a, float x) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
 __device__ __forceinline__ void group_bar(int id) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GROUP) : "memory");
 }
@@ -182,6 +210,7 @@ __device__ __forceinline__ void group_bar(int id) {
 
 using namespace tc;
 
+template <bool PROF>
 __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepParams p, int* __restrict__ flags) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -293,7 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         Raw r2 = load_raw(c2);
         uint32_t chunk_n = 0, row_n = 0;
         double bacc = 0.0;
-        const bool prof = p.prof != nullptr && blockIdx.x == 0 && m == 0;
+        const bool prof = PROF && blockIdx.x == 0 && m == 0;
         long long t_empty = 0, t_bempty = 0, t_stg = 0, t_acc = 0, t_start = prof ? clock64() : 0, tt = 0;
         long long t_issue = 0, t_xform = 0, t_bar = 0, t_mma = 0, t2 = 0;
         while (c0.r < rows) {
@@ -358,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         // =============================== GRAM MMA ISSUE ===============================
         if (lane == 0) {
             uint32_t chunk_n = 0, row_n = 0;
-            const bool prof = p.prof != nullptr && blockIdx.x == 0;
+            const bool prof = PROF && blockIdx.x == 0;
             long long t_full = 0, t_accempty = 0, t_start = prof ? clock64() : 0, tt = 0;
             for (int64_t r = first; r < rows; r += step) {
                 const int64_t row = p.row_order ? p.row_order[r] : r;
@@ -401,24 +430,23 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         }
     } else {
         // =============================== SOLVE (matrix resident in TMEM) ===============================
+        // Block Gauss-Jordan on the 128x128 system, 8 columns per step (see the header): no back
+        // substitution and nothing is written back to TMEM.
         const int g = (warp - SOLVER_WARP0) >> 2;
         const int q = warp & 3;        // TMEM lane quarter this warp may access
         const int t = q * 32 + lane;   // matrix row owned by this thread = TMEM lane
         const int bar_id = 1 + g;
-        uint8_t* gs = smem + OFF_GROUPS + g * GROUP_BYTES;
-        uint8_t* tileH = gs + G_OFF_TILEH;
-        uint8_t* tileL = gs + G_OFF_TILEL;
-        float* Dblk = reinterpret_cast<float*>(gs + G_OFF_DBLK);
-        float* bblk = reinterpret_cast<float*>(gs + G_OFF_BBLK);
-        float* red = reinterpret_cast<float*>(gs + G_OFF_RED);
-        float* dinv = reinterpret_cast<float*>(gs + G_OFF_DINV);
+        const uint32_t gs = smem_base + OFF_GROUPS + g * GROUP_BYTES;
+        const uint32_t tileH = gs + G_OFF_TILEH, tileL = gs + G_OFF_TILEL;
+        const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * F);
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
-        const uint64_t descH = umma_desc_panel(smem_u32(tileH)), descL = umma_desc_panel(smem_u32(tileL));
+        const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
         const float* Grow = p.G + t * F;
         uint32_t row_n = 0, my_rows = 0, panel_n = 0;
-        const bool prof = p.prof != nullptr && blockIdx.x == 0 && g == 0 && t == 0;
+        const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
+        long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0;
         for (int64_t r = first; r < rows; r += step) {
             const int64_t row = p.row_order ? p.row_order[r] : r;
             if (row < 0) continue;
@@ -435,211 +463,171 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
             ++my_rows;
             if (prof) tt = clock64();
             mbar_wait(bar_b_full(g), ph);
-            float bt = bvec[g * F + t];
+            float bt = lds1(smem_base + OFF_BVEC + (g * F + t) * 4);
             mbar_arrive(bar_b_empty(g));
             mbar_wait(bar_acc_full(g), ph);
             tc_fence_after();
             if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
-            bool ok = true;
-            // ------------------------------ factorisation, 16 panels ------------------------------
 #pragma unroll 1
             for (int c0 = 0; c0 < F; c0 += NB) {
                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(Grow + c0));
                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(Grow + c0 + 4));
-                if (c0 > 0) {  // trailing update of the previous panel has landed in TMEM
+                if (prof) t3 = clock64();
+                if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
                     mbar_wait(bar_panel(g), panel_n & 1u);
                     ++panel_n;
                     tc_fence_after();
                 }
+                if (prof) { t4 = clock64(); ph_wait += t4 - t3; }
                 float a[NB];
                 tmem_ld8(t_row + c0, a);
+                if (c0 + NB == F) {  // last read of the accumulator: the Gram of this group's next row may start
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty(g));
+                }
                 a[0] = __fadd_rn(a[0], g0.x); a[1] = __fadd_rn(a[1], g0.y); a[2] = __fadd_rn(a[2], g0.z);
                 a[3] = __fadd_rn(a[3], g0.w); a[4] = __fadd_rn(a[4], g1.x); a[5] = __fadd_rn(a[5], g1.y);
                 a[6] = __fadd_rn(a[6], g1.z); a[7] = __fadd_rn(a[7], g1.w);
+                if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
                 const int rel = t - c0;
-                if (rel >= 0 && rel < NB) {
-                    *reinterpret_cast<float4*>(Dblk + rel * NB) = make_float4(a[0], a[1], a[2], a[3]);
-                    *reinterpret_cast<float4*>(Dblk + rel * NB + 4) = make_float4(a[4], a[5], a[6], a[7]);
-                    bblk[rel] = bt;
+                const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
+                if (q == (c0 >> 5)) {
+                    // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
+                    if (rel >= 0 && rel < NB) {
+                        sts4(Dblk + rel * 32, a[0], a[1], a[2], a[3]);
+                        sts4(Dblk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
+                        sts1(Dblk + 256 + rel * 4, bt);
+                    }
+                    __syncwarp();
+                    float d[36], bb[NB];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const float4 d0 = lds4(Dblk + i * 32);
+                        d[TRI(i, 0)] = d0.x;
+                        if (i >= 1) d[TRI(i, 1)] = d0.y;
+                        if (i >= 2) d[TRI(i, 2)] = d0.z;
+                        if (i >= 3) d[TRI(i, 3)] = d0.w;
+                        if (i >= 4) {
+                            const float4 d1 = lds4(Dblk + i * 32 + 16);
+                            d[TRI(i, 4)] = d1.x;
+                            if (i >= 5) d[TRI(i, 5)] = d1.y;
+                            if (i >= 6) d[TRI(i, 6)] = d1.z;
+                            if (i >= 7) d[TRI(i, 7)] = d1.w;
+                        }
+                    }
+                    {
+                        const float4 b0 = lds4(Dblk + 256), b1 = lds4(Dblk + 272);
+                        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+                        bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+                    }
+                    Factor8 fo;
+                    const bool ok = factor8(d, bb, fo);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) {
+                            sts4(nd + i * 32, fo.n[TRI(i, 0)], i >= 1 ? fo.n[TRI(i, 1)] : 0.f, i >= 2 ? fo.n[TRI(i, 2)] : 0.f,
+                                 i >= 3 ? fo.n[TRI(i, 3)] : 0.f);
+                            if (i >= 4)
+                                sts4(nd + i * 32 + 16, fo.n[TRI(i, 4)], i >= 5 ? fo.n[TRI(i, 5)] : 0.f,
+                                     i >= 6 ? fo.n[TRI(i, 6)] : 0.f, i >= 7 ? fo.n[TRI(i, 7)] : 0.f);
+                        }
+                        sts4(zd, fo.zb[0], fo.zb[1], fo.zb[2], fo.zb[3]);
+                        sts4(zd + 16, fo.zb[4], fo.zb[5], fo.zb[6], fo.zb[7]);
+                        if (!ok) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
+                    }
+                    if (prof) { t4 = clock64(); ph_own += t4 - t3; }
                 }
                 group_bar(bar_id);
-                // 8x8 diagonal block: factored redundantly by every thread (no communication in the chain)
-                float L[NB][NB], rinv[NB], zb[NB];
+                // ---- every row outside the block: P = a N^T, rhs -= P zb; the block's own rows are pivots (P = 0) ----
+                float P[NB];
                 {
-                    float D[NB][NB];
-#pragma unroll
-                    for (int rr = 0; rr < NB; ++rr) {
-                        const float4 d0 = *reinterpret_cast<const float4*>(Dblk + rr * NB);
-                        const float4 d1 = *reinterpret_cast<const float4*>(Dblk + rr * NB + 4);
-                        D[rr][0] = d0.x; D[rr][1] = d0.y; D[rr][2] = d0.z; D[rr][3] = d0.w;
-                        D[rr][4] = d1.x; D[rr][5] = d1.y; D[rr][6] = d1.z; D[rr][7] = d1.w;
-                    }
-                    const float4 b0 = *reinterpret_cast<const float4*>(bblk);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bblk + 4);
-                    const float bb[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    const bool pivot = rel >= 0 && rel < NB;
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
-                        float sd = D[j][j];
-#pragma unroll
-                        for (int k = 0; k < j; ++k) sd = fmaf(-L[j][k], L[j][k], sd);
-                        ok = ok && (sd > 0.0f);
-                        float ri = rsqrtf(sd);
-                        ri = ri * fmaf(-0.5f * sd, ri * ri, 1.5f);  // one Newton step: ~1 ulp
-                        rinv[j] = ri;
-                        L[j][j] = sd * ri;
-#pragma unroll
-                        for (int i = j + 1; i < NB; ++i) {
-                            float v = D[i][j];
-#pragma unroll
-                            for (int k = 0; k < j; ++k) v = fmaf(-L[i][k], L[j][k], v);
-                            L[i][j] = v * ri;
+                        const float4 n0 = lds4(nd + j * 32);
+                        float v = a[0] * n0.x;
+                        if (j >= 1) v = fmaf(a[1], n0.y, v);
+                        if (j >= 2) v = fmaf(a[2], n0.z, v);
+                        if (j >= 3) v = fmaf(a[3], n0.w, v);
+                        if (j >= 4) {
+                            const float4 n1 = lds4(nd + j * 32 + 16);
+                            v = fmaf(a[4], n1.x, v);
+                            if (j >= 5) v = fmaf(a[5], n1.y, v);
+                            if (j >= 6) v = fmaf(a[6], n1.z, v);
+                            if (j >= 7) v = fmaf(a[7], n1.w, v);
                         }
-                        float zz = bb[j];  // forward substitution of the block's rhs
-#pragma unroll
-                        for (int k = 0; k < j; ++k) zz = fmaf(-L[j][k], zb[k], zz);
-                        zb[j] = zz * ri;
+                        P[j] = pivot ? 0.0f : v;
                     }
+                    const float4 z0 = lds4(zd), z1 = lds4(zd + 16);
+                    float u0 = P[0] * z0.x, u1 = P[1] * z0.y;  // two chains, fixed order
+                    u0 = fmaf(P[2], z0.z, u0); u1 = fmaf(P[3], z0.w, u1);
+                    u0 = fmaf(P[4], z1.x, u0); u1 = fmaf(P[5], z1.y, u1);
+                    u0 = fmaf(P[6], z1.z, u0); u1 = fmaf(P[7], z1.w, u1);
+                    bt -= u0 + u1;
                 }
-                // own row against the block
-                float l[NB];
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    float v = a[j];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) v = fmaf(-l[k], L[j][k], v);
-                    v *= rinv[j];
-                    l[j] = (rel < 0 || j > rel) ? 0.0f : v;  // dead rows; nothing right of the diagonal
-                }
-                if (rel >= NB) {
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) bt = fmaf(-l[k], zb[k], bt);
-                } else if (rel >= 0) {
-#pragma unroll
-                    for (int j = 0; j < NB; ++j)
-                        if (rel == j) bt = zb[j];  // z of this row is final
-                }
-                if (rel == 0) {
-                    *reinterpret_cast<float4*>(dinv + c0) = make_float4(rinv[0], rinv[1], rinv[2], rinv[3]);
-                    *reinterpret_cast<float4*>(dinv + c0 + 4) = make_float4(rinv[4], rinv[5], rinv[6], rinv[7]);
-                }
-                tmem_st8(t_row + c0, l);  // finished L over the dead columns (back substitution reads it)
                 if (c0 + NB < F) {
                     float lh[NB], ll[NB];
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
-                        const float v = rel >= NB ? l[j] : 0.0f;  // only rows below the block take part
-                        lh[j] = tf32_round(v);
-                        ll[j] = tf32_round(v - lh[j]);
+                        lh[j] = tf32_round(P[j]);
+                        ll[j] = tf32_round(P[j] - lh[j]);
                     }
-                    const int o = (t >> 3) * 256 + (t & 7) * 16;
-                    *reinterpret_cast<float4*>(tileH + o) = make_float4(lh[0], lh[1], lh[2], lh[3]);
-                    *reinterpret_cast<float4*>(tileH + o + 128) = make_float4(lh[4], lh[5], lh[6], lh[7]);
-                    *reinterpret_cast<float4*>(tileL + o) = make_float4(ll[0], ll[1], ll[2], ll[3]);
-                    *reinterpret_cast<float4*>(tileL + o + 128) = make_float4(ll[4], ll[5], ll[6], ll[7]);
+                    const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+                    sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
+                    sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
+                    sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
+                    sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
                     fence_async_smem();
-                }
-                tc_fence_before();
-                group_bar(bar_id);
-                if (c0 + NB < F && t == 0) {  // S -= L L^T on the whole accumulator (dead rows/columns are zero)
-                    tc_fence_after();
-                    umma_tf32(d_tmem, descH, descH, IDESC_TF32_M128_N128_NEG, 1u);
-                    umma_tf32(d_tmem, descH, descL, IDESC_TF32_M128_N128_NEG, 1u);
-                    umma_tf32(d_tmem, descL, descH, IDESC_TF32_M128_N128_NEG, 1u);
-                    tc_commit(bar_panel(g));
+                    tc_fence_before();
+                    if (prof) t3 = clock64();
+                    group_bar(bar_id);
+                    if (t == 0) {
+                        // S[:, j] -= P P[j]^T for the live columns j >= c0 + 8 (all 128 rows: Gauss-Jordan)
+                        tc_fence_after();
+                        if (prof) { t4 = clock64(); ph_p += t4 - t3; }
+                        const uint32_t start = (uint32_t)((c0 + NB) >> 4) << 4;
+                        const uint32_t idesc = IDESC_TF32_NEG_M128 | (((F - start) >> 3) << 17);
+                        const uint64_t bH = descH + (uint64_t)(start * 2), bL = descL + (uint64_t)(start * 2);
+                        umma_tf32(d_tmem + start, descH, bH, idesc, 1u);
+                        umma_tf32(d_tmem + start, descH, bL, idesc, 1u);
+                        umma_tf32(d_tmem + start, descL, bH, idesc, 1u);
+                        tc_commit(bar_panel(g));
+                        if (prof) ph_issue += clock64() - t4;
+                    }
                 }
             }
             if (prof) { t_fact += clock64() - tt; tt = clock64(); }
-            // ------------------------------ back substitution  L^T x = z ------------------------------
-            // Row-oriented: x_t = (z_t - sum_{i>t} L[i][t] x_i) / L[t][t]. Thread i re-reads its own 8 panel
-            // values from its TMEM lane, contributes L[i][c0+j] * x_i, and the 8 sums are reduced over the
-            // group (shuffle tree + 4 partials in shared memory, fixed order). One barrier per block.
-            float xt = 0.0f;
-#pragma unroll 1
-            for (int c0 = F - NB; c0 >= 0; c0 -= NB) {
-                const int par = (c0 >> 3) & 1;
-                float l[NB];
-                tmem_ld8(t_row + c0, l);
-                const int rel = t - c0;
-                float cj[NB];
+            // ---- the system is block diagonal now: x_blk = (L L^T)^-1 b_blk = N^T (N b_blk) ----
+            sts1(bfin + t * 4, bt);
+            group_bar(bar_id);
+            {
+                const int r8 = t & 7;
+                const uint32_t nb = Nst + (t >> 3) * 256, bq = bfin + (t >> 3) * 32;
+                const float4 b0 = lds4(bq), b1 = lds4(bq + 16);
+                const float bb[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float xt = 0.0f;
 #pragma unroll
-                for (int j = 0; j < NB; ++j) cj[j] = rel >= NB ? l[j] * xt : 0.0f;
-                // transpose-reduce over the warp: 9 shuffles instead of 40; afterwards lane holds the
-                // warp sum of column jsel = 4*bit4 + 2*bit3 + bit2 of its lane id (fixed order)
-                float w4[4], w2[2], w1;
-                {
-                    const bool hi = lane & 16;
+                for (int j = 0; j < NB; ++j) {
+                    const float4 n0 = lds4(nb + j * 32), n1 = lds4(nb + j * 32 + 16);
+                    const float nr[NB] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                    float y = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float send = hi ? cj[j] : cj[4 + j];
-                        const float keep = hi ? cj[4 + j] : cj[j];
-                        w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-                    const bool h8 = lane & 8;
+                    for (int k = 0; k <= j; ++k) y = fmaf(nr[k], bb[k], y);
+                    float nsel = 0.0f;  // N[j][r8] (zero above the diagonal)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const float send = h8 ? w4[j] : w4[2 + j];
-                        const float keep = h8 ? w4[2 + j] : w4[j];
-                        w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    const bool h4 = lane & 4;
-                    const float send = h4 ? w2[0] : w2[1];
-                    const float keep = h4 ? w2[1] : w2[0];
-                    w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
-                    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                    for (int k = 0; k <= j; ++k) nsel = (k == r8) ? nr[k] : nsel;
+                    xt = fmaf(nsel, y, xt);
                 }
-                if ((lane & 3) == 0) red[(par * 4 + q) * NB + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = w1;
-                if (rel >= 0 && rel < NB) {
-                    *reinterpret_cast<float4*>(Dblk + par * 64 + rel * NB) = make_float4(l[0], l[1], l[2], l[3]);
-                    *reinterpret_cast<float4*>(Dblk + par * 64 + rel * NB + 4) = make_float4(l[4], l[5], l[6], l[7]);
-                    bblk[par * NB + rel] = bt;
-                }
-                group_bar(bar_id);
-                if (q == (c0 >> 5)) {  // only the warp that owns the block solves it; x_t stays in its lanes
-                    float x[NB], sj[NB];
-                    {
-                        const float4 z0 = *reinterpret_cast<const float4*>(bblk + par * NB);
-                        const float4 z1 = *reinterpret_cast<const float4*>(bblk + par * NB + 4);
-                        sj[0] = z0.x; sj[1] = z0.y; sj[2] = z0.z; sj[3] = z0.w;
-                        sj[4] = z1.x; sj[5] = z1.y; sj[6] = z1.z; sj[7] = z1.w;
-                    }
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const float4 p0 = *reinterpret_cast<const float4*>(red + (par * 4 + w) * NB);
-                        const float4 p1 = *reinterpret_cast<const float4*>(red + (par * 4 + w) * NB + 4);
-                        sj[0] -= p0.x; sj[1] -= p0.y; sj[2] -= p0.z; sj[3] -= p0.w;
-                        sj[4] -= p1.x; sj[5] -= p1.y; sj[6] -= p1.z; sj[7] -= p1.w;
-                    }
-                    const float4 r0 = *reinterpret_cast<const float4*>(dinv + c0);
-                    const float4 r1 = *reinterpret_cast<const float4*>(dinv + c0 + 4);
-                    const float ri[NB] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                    float Lb[NB][NB];
-#pragma unroll
-                    for (int rr = 0; rr < NB; ++rr) {
-                        const float4 d0 = *reinterpret_cast<const float4*>(Dblk + par * 64 + rr * NB);
-                        const float4 d1 = *reinterpret_cast<const float4*>(Dblk + par * 64 + rr * NB + 4);
-                        Lb[rr][0] = d0.x; Lb[rr][1] = d0.y; Lb[rr][2] = d0.z; Lb[rr][3] = d0.w;
-                        Lb[rr][4] = d1.x; Lb[rr][5] = d1.y; Lb[rr][6] = d1.z; Lb[rr][7] = d1.w;
-                    }
-#pragma unroll
-                    for (int j = NB - 1; j >= 0; --j) {
-                        float v = sj[j];
-#pragma unroll
-                        for (int rr = j + 1; rr < NB; ++rr) v = fmaf(-Lb[rr][j], x[rr], v);
-                        x[j] = v * ri[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < NB; ++j)
-                        if (rel == j) xt = x[j];
-                }
+                xout[t] = xt;
             }
-            tc_fence_before();
-            mbar_arrive(bar_acc_empty(g));  // accumulator g is free for the Gram of this group's next row
-            if (ok) xout[t] = xt;
-            else if (t == 0) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
+            group_bar(bar_id);  // Nst / bfin are rewritten by the next row
             if (prof) t_back += clock64() - tt;
         }
-        if (prof) { p.prof[16] = clock64() - t_start; p.prof[17] = t_accfull; p.prof[18] = t_fact; p.prof[19] = t_back; p.prof[22] = my_rows; }
+        if (prof) {
+            p.prof[16] = clock64() - t_start; p.prof[17] = t_accfull; p.prof[18] = t_fact; p.prof[19] = t_back;
+            p.prof[22] = my_rows; p.prof[24] = ph_wait; p.prof[25] = ph_ld; p.prof[26] = ph_own; p.prof[28] = ph_p;
+            p.prof[31] = ph_issue;
+        }
     }
     // =============================== TEARDOWN ===============================
     tc_fence_before();
@@ -652,7 +640,10 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
 
 bool tc_half_step_supported(int f, int bias) { return f == tc::F && !bias; }
 
-size_t tc_half_step_workspace_bytes(int64_t, int f, int) { return simt_half_step_workspace_bytes(f); }
+size_t tc_half_step_workspace_bytes(int64_t, int f, int) {  // header + profile slots (f = 128 needs no SIMT slab)
+    const size_t a = simt_half_step_workspace_bytes(f);
+    return a > 1024 ? a : 1024;
+}
 
 int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st) {
     const size_t need = tc_half_step_workspace_bytes(in.rows, in.f, in.bias);
@@ -660,14 +651,16 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
         set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu", ws_bytes, need);
         return WMF_ERR_WORKSPACE;
     }
-    WMF_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+    WMF_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
     int* flags = reinterpret_cast<int*>(ws) + 1;  // [0] = SIMT row counter, [1] = redo flags
-    WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     HalfStepParams p = in;
-    p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 64) : nullptr;
+    p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 256) : nullptr;
     int grid = sm_count();
     if ((int64_t)grid > in.rows) grid = (int)in.rows;
-    als_half_step_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p, flags);
+    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, flags);
+    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, flags);
     WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
     // fix-up: runs the FP32/LU kernel over the whole half-step only if a flag was raised
     HalfStepParams fix = in;

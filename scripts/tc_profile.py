@@ -17,7 +17,7 @@ def run(csr, Yd, name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); X = engine.half_step(csr, Yd, G, algo=_lib.ALGO_TCGEN05); e1.record(); torch.cuda.synchronize()
     ws = engine.workspace(0, dev)
-    prof = ws[64:256].view(torch.int64).cpu().numpy()
+    prof = ws[256:256 + 512].view(torch.int64).cpu().numpy()
     flags = ws[0:8].view(torch.int32).cpu().numpy()
     ms = e0.elapsed_time(e1)
     print(f"{name}: {ms:.2f} ms  flags={flags}")
@@ -25,8 +25,9 @@ def run(csr, Yd, name):
     print("  gather total", f(prof[0]), "wait_empty", f(prof[1]), "wait_bempty", f(prof[2]), "chunks", prof[3], "rows", prof[4])
     print("  mma total", f(prof[8]), "wait_full", f(prof[9]), "wait_accempty", f(prof[10]))
     print("  solver0 total", f(prof[16]), "wait(b,acc)full", f(prof[17]), "factor", f(prof[18]), "backsub", f(prof[19]), "rows", prof[22])
-    print("  factor phases: wait_mma", f(prof[7]), "tmem_ld", f(prof[15]), "bar1", f(prof[20]), "chol+trsm", f(prof[21]), "st+split", f(prof[23]), "bar2", f(prof[11]), "mma_issue", f(prof[12]))
-    print("  backsub phases: tmem_ld", f(prof[13]), "reduce", f(prof[14]), "bar", f(prof[5]), "solve", f(prof[6]))
+    print("  gather phases: issue", f(prof[11]), "wait_stg", f(prof[5]), "xform", f(prof[12]), "arrive", f(prof[13]))
+    print("  solver phases (thread 0 of group 0): wait_mma", f(prof[24]), "tmem_ld", f(prof[25]), "own_factor(4 of 16 panels)", f(prof[26]),
+          "barA", f(prof[27]), "P", f(prof[28]), "split+sts+fence", f(prof[29]), "barB", f(prof[30]), "mma_issue", f(prof[31]))
     return X
 U = run(Cd, Y, "user half-step")
 run(CT, U, "item half-step")
