@@ -3,32 +3,39 @@
 //
 // Per CSR row r:  A_r = G + sum_j d_j y_j y_j^T  (128x128, K = n_r),  b_r = sum_j (d_j+1) y_j,
 // x_r = A_r^-1 b_r.  Everything O(f^2) per entry and O(f^3) per row runs on the 5th-gen tensor
-// cores with FP32-equivalent accuracy (3xTF32: plain TF32 fails the 1e-4 bar):
+// cores with FP32-equivalent accuracy (single-pass TF32/BF16 fails the 1e-4 bar):
 //
-//   Gram      z_j = sqrt(d_j) y_j = zh + zl (both TF32-exact);  W = sum zh zh^T + zh zl^T + zl zh^T
-//             -> three tcgen05.mma (kind::tf32, M=N=128, K=8) per 8 stored entries into a
-//             128-column fp32 TMEM accumulator; operand tiles K-major, 128-byte swizzled.
-//   Cholesky  the matrix STAYS in TMEM. Panels of 8 columns: each thread (= TMEM lane = matrix
-//             row) loads its 8 panel entries (tcgen05.ld), adds G lazily, the 8x8 diagonal block
-//             is factored in registers, the row is solved against it, the panel L (hi/lo split)
-//             goes to shared memory as an MMA operand and the rank-8 trailing update
-//             S -= L L^T is again three tcgen05.mma (negated A) on the whole 128x128 accumulator.
-//             The right-hand side rides along in registers (forward substitution fused);
-//             the finished L is written back over the dead columns (tcgen05.st) and read once
-//             more, 8 rows at a time, for the back substitution.
+//   Gram    z_j = S sqrt(d_j) y_j = zh + zl, both halves FP16 (11-bit significands, like TF32, but
+//           K = 16 per instruction instead of 8); S is a power of two chosen per half-step from
+//           max diag(G) (>= max y^2) and max|d| so that zh never overflows FP16 and zl stays a normal
+//           number for every entry that matters. W = sum zh zh^T + zh zl^T + zl zh^T: three
+//           tcgen05.mma (kind::f16, M = N = 128, K = 16) per 16 stored entries into a 128-column
+//           fp32 TMEM accumulator; operand tiles K-major, 128-byte swizzled.
+//   Solve   block Gauss-Jordan, the matrix STAYS in TMEM. Steps of 8 columns: every thread
+//           (= TMEM lane = matrix row) loads its 8 entries of the pivot columns (tcgen05.ld), adds G
+//           lazily; the warp that owns the 8 pivot rows factors the 8x8 pivot block (Cholesky, straight-
+//           line code) and publishes N = L^-1; every other row forms P = a N^T, updates its right-hand
+//           side, writes P (TF32 hi/lo split) to shared memory as an MMA operand and the rank-8 update
+//           S -= P P^T of ALL rows (above and below the pivots) is three tcgen05.mma (kind::tf32, negated
+//           A, N trimmed to the live columns). After 16 steps the system is block diagonal and
+//           x_blk = N^T N b_blk: no back substitution, nothing is written back to TMEM.
 //
 // TMEM holds four such matrices (4 x 128 = 512 columns): four solver groups of 128 threads each
 // own one accumulator, so while one row is in its pivot chain three others fill the issue slots.
 // One persistent CTA per SM, warp-specialised, all hand-offs through mbarriers:
-//   warps 0-3   gather   thread m owns feature m: loads Y[idx_j][m] for 32 entries (one coalesced
-//               128-B line per warp and entry), forms zh/zl, stores them with the XOR swizzle a TMA
-//               load would have produced (TMA cannot: the operand is gathered, scaled and split),
-//               keeps the rhs b[m] in registers.
-//   warps 4-19  solve    group g = (warp-4)/4 owns accumulator g and the rows n with n % 4 == g.
-//   warp 20     MMA      one thread issues the Gram MMAs and commits stage/accumulator barriers.
+//   warps 0-15  solve    group g = warp/4 owns accumulator g and the rows n with n % 4 == g.
+//   warps 16-23 gather   two teams of 128 threads; a team takes every other 32-entry sub-chunk of a
+//               row. Thread m owns feature m: the 32 gathered factor rows land in a raw staging buffer
+//               with cp.async (one coalesced 512-B row per warp instruction, three sub-chunks in
+//               flight per team), thread m reads column m, scales, splits to FP16 hi/lo and stores
+//               the K-major swizzled operand tiles a TMA load would have produced (TMA cannot: the
+//               operand is gathered, scaled and split); the rhs partial b[m] stays in registers.
+//   warp 24     MMA      one thread issues the Gram MMAs (at most two K-steps queued, so the solvers'
+//               rank-8 updates never wait behind a long burst) and commits stage/accumulator barriers.
 //
-// Rows whose weights are negative (sqrt undefined) or whose Cholesky meets a non-positive
-// pivot raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).
+// Rows whose weights are negative (sqrt undefined) or whose pivot block is not positive definite
+// raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "half_step.cuh"
@@ -39,18 +46,20 @@ namespace wmf {
 namespace tc {
 
 constexpr int F = 128;               // factor width handled by this kernel
-constexpr int CHUNK = 32;            // stored entries per staged tile (= one 128-byte swizzle row)
-constexpr int NSTAGE = 3;            // operand-tile stages
-constexpr int NSTG = 3;              // raw gather staging buffers (cp.async depth)
-constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 32 fp32 (K) = 16 KB
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // [zh ; zl]
-constexpr int STG_BYTES = CHUNK * F * 4;     // 32 gathered factor rows, row-major, 16 KB
-constexpr int NB = 8;                // Cholesky panel width
+constexpr int SUB = 32;              // stored entries per sub-chunk (one pipeline stage)
+constexpr int NSTAGE = 4;            // operand stages (two sub-chunks share one 128-byte-swizzled tile pair)
+constexpr int NTEAM = 2;             // gather teams
+constexpr int NSTG = 3;              // raw staging buffers per team (cp.async depth)
+constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 64 fp16 (K) = 16 KB, holds two sub-chunks
+constexpr int PAIR_BYTES = 2 * TILE_BYTES;   // [zh ; zl]
+constexpr int STG_BYTES = SUB * F * 4;       // 32 gathered factor rows, row-major fp32, 16 KB
+constexpr int META_BYTES = SUB * 8;          // S*sqrt(d) [32] then d+1 [32]
+constexpr int NB = 8;                // Gauss-Jordan step width
 constexpr int NGROUP = 4;            // solver groups = TMEM accumulators
 constexpr int GROUP = 128;
-constexpr int GATHER_THREADS = 128;
-constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WARP0 + 4;  // high warp ids issue first
-constexpr int THREADS = (MMA_WARP + 1) * 32;               // 672
+constexpr int TEAM = 128;
+constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WARP0 + NTEAM * 4;  // high warp ids issue first
+constexpr int THREADS = (MMA_WARP + 1) * 32;               // 800
 constexpr uint32_t TMEM_COLS = 512;
 static_assert(NGROUP * F <= 512, "TMEM columns");
 
@@ -65,17 +74,26 @@ constexpr int G_OFF_BFIN = G_OFF_DBLK + (NB * NB + 2 * NB) * 4;     // 128 float
 constexpr int GROUP_BYTES = ((G_OFF_BFIN + F * 4 + 127) / 128) * 128;
 
 // shared memory carve-up (bytes from a 1024-aligned base)
-constexpr int OFF_STAGES = 0;
-constexpr int OFF_STG = OFF_STAGES + NSTAGE * STAGE_BYTES;
-constexpr int OFF_META = OFF_STG + NSTG * STG_BYTES;                // NSTG x 32 x float2
-constexpr int OFF_GROUPS = OFF_META + NSTG * CHUNK * 8;
-constexpr int OFF_BVEC = OFF_GROUPS + NGROUP * GROUP_BYTES;         // NGROUP x F floats
-constexpr int OFF_BARS = OFF_BVEC + NGROUP * F * 4;                 // mbarriers (8 B each)
-constexpr int NBARS = 2 * NSTAGE + NSTG + 5 * NGROUP;
+constexpr int OFF_STAGES = 0;                                        // NSTAGE/2 tile pairs
+constexpr int OFF_STG = OFF_STAGES + (NSTAGE / 2) * PAIR_BYTES;
+constexpr int OFF_META = OFF_STG + NTEAM * NSTG * STG_BYTES;
+constexpr int OFF_GROUPS = ((OFF_META + NTEAM * NSTG * META_BYTES + 127) / 128) * 128;
+constexpr int OFF_BVEC = OFF_GROUPS + NGROUP * GROUP_BYTES;         // NGROUP x NTEAM x F floats
+constexpr int OFF_BARS = OFF_BVEC + NGROUP * NTEAM * F * 4;         // mbarriers (8 B each)
+constexpr int NBARS = 2 * NSTAGE + NTEAM * NSTG + 2 + (4 + NTEAM) * NGROUP;
 constexpr int OFF_TMEM_PTR = OFF_BARS + NBARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                // + slack for alignment
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_GROUPS % 128 == 0 && GROUP_BYTES % 128 == 0 && OFF_BARS % 8 == 0 && OFF_STG % 1024 == 0, "alignment");
+
+// workspace layout (bytes): [0] SIMT row counter, [4] redo flags, [8] max diag(G) bits, [12] max|d| bits,
+// [256, 768) profile slots, [1024, ...) row table
+constexpr size_t WS_PROF = 256, WS_ROWTAB = 1024;
+struct __align__(16) RowEnt {
+    int32_t row;  // CSR row id, -1 = padding slot
+    int32_t n;    // stored entries (0: nothing to do, X row already zeroed)
+    int64_t lo;   // indptr[row]
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -108,7 +126,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256 (cute::UMMA::InstrDescriptor)
+// K-major, no swizzle: 8-row x 16-byte core matrices; the two K-chunks of a row group are
+// LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart (panel operand, K = 8 fp32).
+__device__ __forceinline__ uint64_t umma_desc_panel(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+           (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: fp32 accumulate (bit 4), A/B formats at bits 7/10 (0 = F16, 2 = TF32),
+// bit 13 negates A, N >> 3 at bit 17, M >> 4 at bit 24; K-major A and B.
+constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_TF32_NEG_M128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((128u >> 4) << 24);  // N filled in at issue
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -119,39 +147,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // round-to-nearest (ties away) to the 10-bit TF32 mantissa, done with integer ops
 __device__ __forceinline__ float tf32_round(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-
-
-// K-major, no swizzle: 8-row x 16-byte core matrices; the two K-chunks of a row group are
-// LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart (panel operand, K = 8 fp32).
-__device__ __forceinline__ uint64_t umma_desc_panel(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
-           (1ull << 46);
-}
-// kind::tf32, fp32 accumulate, K-major A and B, M = N = 128; NEG: A negated (trailing update)
-constexpr uint32_t IDESC_TF32_M128_N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t IDESC_TF32_NEG_M128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((128u >> 4) << 24);  // N filled in at issue
-#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -161,14 +170,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
-                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-                 : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -183,11 +184,6 @@ __device__ __forceinline__ float4 lds4(uint32_t a) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ float2 lds2(uint32_t a) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ float lds1(uint32_t a) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -196,14 +192,66 @@ __device__ __forceinline__ float lds1(uint32_t a) {
 __device__ __forceinline__ void sts4(uint32_t a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-__device__ __forceinline__ void sts2(uint32_t a, float x, float y) {
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+__device__ __forceinline__ void sts4u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 __device__ __forceinline__ void sts1(uint32_t a, float x) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
 }
-__device__ __forceinline__ void group_bar(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GROUP) : "memory");
+__device__ __forceinline__ void named_bar(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// S = 2^e with S * sqrt(max diag G) * sqrt(max|d|) just below the FP16 maximum. diag(G) = sum y^2 +
+// lambda bounds every y^2, so zh cannot overflow; the bound is loose by up to sqrt(#rows of Y), which
+// only moves the point below which zl becomes subnormal (entries that small do not matter).
+__device__ __forceinline__ float gram_scale(const float* hdr) {
+    const float m = sqrtf(hdr[2]) * sqrtf(hdr[3]);
+    if (!(m > 0.0f) || !(m < 3.0e38f)) return 1.0f;
+    int e = (int)floorf(log2f(60000.0f / m));
+    e = e > 40 ? 40 : (e < -40 ? -40 : e);  // S^2 and 1/S^2 stay finite
+    return exp2f((float)e);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prep: row table (one 16-byte entry per schedule slot), zero rows without entries, and the maxima
+// that fix the FP16 scale.
+// ---------------------------------------------------------------------------------------------------
+__global__ void tc_prep_rows_kernel(HalfStepParams p, RowEnt* __restrict__ tab) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.sched_len) return;
+    const int64_t row = p.row_order ? p.row_order[s] : s;
+    RowEnt e{-1, 0, 0};
+    if (row >= 0) {
+        const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
+        e.row = (int32_t)row;
+        e.n = (int32_t)(hi - lo);
+        e.lo = lo;
+        if (hi == lo) {  // wmf_model.py:223-225
+            float* x = p.X + row * p.ldx;
+            for (int i = 0; i < F; ++i) x[i] = 0.0f;
+        }
+    }
+    tab[s] = e;
+}
+
+// out[0] = max diag(G) (block 0), out[1] = max |data[indptr[0] .. indptr[rows])|
+__global__ void tc_maxima_kernel(HalfStepParams p, uint32_t* __restrict__ out) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        float m = 0.0f;
+        for (int i = threadIdx.x; i < F; i += 32) m = fmaxf(m, fabsf(p.G[i * F + i]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(out, __float_as_uint(m));
+    }
+    const int64_t lo = p.indptr[0], hi = p.indptr[p.rows];
+    float m = 0.0f;
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(p.data[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out + 1, __float_as_uint(m));  // order-preserving for m >= 0
 }
 
 }  // namespace tc
@@ -211,189 +259,228 @@ __device__ __forceinline__ void group_bar(int id) {
 using namespace tc;
 
 template <bool PROF>
-__global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepParams p, int* __restrict__ flags) {
+__global__ void __launch_bounds__(THREADS, 1)
+als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, const float* __restrict__ hdr,
+                        int* __restrict__ flags) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t smem_base = smem_u32(smem);
-    float* bvec = reinterpret_cast<float*>(smem + OFF_BVEC);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = smem_base + OFF_BARS;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
-    auto bar_stg = [&](int s) { return bars + 8u * (2 * NSTAGE + s); };
-    auto bar_acc_full = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + g); };
-    auto bar_acc_empty = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + NGROUP + g); };
-    auto bar_b_full = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + 2 * NGROUP + g); };
-    auto bar_b_empty = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + 3 * NGROUP + g); };
-    auto bar_panel = [&](int g) { return bars + 8u * (2 * NSTAGE + NSTG + 4 * NGROUP + g); };
+    auto bar_stg = [&](int team, int s) { return bars + 8u * (2 * NSTAGE + team * NSTG + s); };
+    auto bar_thr = [&](int x) { return bars + 8u * (2 * NSTAGE + NTEAM * NSTG + x); };
+    constexpr int B0 = 2 * NSTAGE + NTEAM * NSTG + 2;
+    auto bar_acc_full = [&](int g) { return bars + 8u * (B0 + g); };
+    auto bar_acc_empty = [&](int g) { return bars + 8u * (B0 + NGROUP + g); };
+    auto bar_b_empty = [&](int g) { return bars + 8u * (B0 + 2 * NGROUP + g); };
+    auto bar_panel = [&](int g) { return bars + 8u * (B0 + 3 * NGROUP + g); };
+    auto bar_b_full = [&](int g, int team) { return bars + 8u * (B0 + 4 * NGROUP + g * NTEAM + team); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), GATHER_THREADS); mbar_init(bar_empty(s), 1); }
-        for (int s = 0; s < NSTG; ++s) mbar_init(bar_stg(s), GATHER_THREADS);
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), TEAM); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < NTEAM * NSTG; ++s) mbar_init(bar_stg(0, s), TEAM);
+        mbar_init(bar_thr(0), 1);
+        mbar_init(bar_thr(1), 1);
         for (int g = 0; g < NGROUP; ++g) {
             mbar_init(bar_acc_full(g), 1);
             mbar_init(bar_acc_empty(g), GROUP);
-            mbar_init(bar_b_full(g), GATHER_THREADS);
             mbar_init(bar_b_empty(g), GROUP);
             mbar_init(bar_panel(g), 1);
+            for (int tm = 0; tm < NTEAM; ++tm) mbar_init(bar_b_full(g, tm), TEAM);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const uint32_t tmem_ptr_addr = smem_base + OFF_TMEM_PTR;
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
                      "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-    const int64_t rows = p.sched_len;  // schedule slots; slot s belongs to CTA s % gridDim
-    const int64_t first = blockIdx.x, step = gridDim.x;
+    // slot k of this CTA = schedule slot k * gridDim + blockIdx
+    const int nslots = (int)((p.sched_len - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const RowEnt* mytab = rowtab + blockIdx.x;
+    const int64_t tstep = gridDim.x;
+    auto ent_at = [&](int k) -> RowEnt {
+        RowEnt e{-1, 0, 0};
+        if (k < nslots) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(mytab + (int64_t)k * tstep));
+            e.row = v.x; e.n = v.y; e.lo = ((int64_t)(uint32_t)v.z) | ((int64_t)v.w << 32);
+        }
+        return e;
+    };
+    const float S = gram_scale(hdr);
 
     if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
-        // =============================== GATHER + GRAM MMA ISSUE ===============================
-        // Flattened (row, chunk) sequence of this CTA, three chunks deep:
-        //   chunk i+3: index/weight of the entries -> registers (lanes 0-7 of each warp, 8 entries per warp)
-        //   chunk i+2: 32 x 512-B factor rows -> raw staging buffer with cp.async (16 B per lane,
-        //              one coalesced row per warp instruction, no registers held), completion on an mbarrier
-        //   chunk i  : thread m reads column m of the staged rows, scales, splits to TF32 hi/lo, stores the
-        //              K-major swizzled operand tiles; after the gather barrier thread 0 issues the MMAs.
-        const int m = tid - GATHER_WARP0 * 32;  // feature index
-        const int gw = warp - GATHER_WARP0;     // gather warp 0..3
-        struct Cursor {
-            int64_t r, base, hi;  // position in the CTA's row list, first entry of the chunk, row end
-        };
-        auto seek = [&](Cursor& c) {  // move c.r forward to the next non-empty row (or past the end)
-            while (c.r < rows) {
-                const int64_t row = p.row_order ? p.row_order[c.r] : c.r;
-                if (row >= 0) {  // -1 = padding slot of the balanced schedule
-                    const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-                    if (lo != hi) { c.base = lo; c.hi = hi; return; }
+        // =============================== GATHER ===============================
+        // Team T walks the rows of this CTA and takes the sub-chunks c with (c + row_n + T) even. Three
+        // of its sub-chunks are in flight: j+3 index/weight -> registers (lanes 0-7 of each warp), j+2
+        // factor rows -> raw staging buffer (cp.async), j -> operand tiles.
+        const int team = (warp - GATHER_WARP0) >> 2;
+        const int m = (tid - GATHER_WARP0 * 32) & (TEAM - 1);  // feature index
+        const int gw = (warp - GATHER_WARP0) & 3;              // warp within the team
+        // cursor: the team's next sub-chunk, three steps ahead of the transform
+        int cu_k = -1;        // CTA-local slot of the current row
+        int cu_row_n = -1;    // index of the row among this CTA's non-empty rows
+        int cu_c = 0, cu_nsub = 0, cu_n = 0, cu_gi0 = 0;  // sub-chunk in row, sub-chunks / entries of the row, global index of sub-chunk 0
+        int64_t cu_lo = 0;    // first entry of the row
+        RowEnt w0 = ent_at(0), w1 = ent_at(1);  // prefetched table entries k+1, k+2
+        auto advance = [&](bool first) {  // to the team's next sub-chunk
+            if (!first) cu_c += 2;
+            while (cu_k < nslots && cu_c >= cu_nsub) {
+                bool found = false;
+                while (!found) {  // next non-empty row
+                    ++cu_k;
+                    if (cu_k >= nslots) break;
+                    const RowEnt e = w0;
+                    w0 = w1;
+                    w1 = ent_at(cu_k + 2);
+                    if (e.n > 0) {
+                        cu_gi0 += cu_nsub;
+                        ++cu_row_n;
+                        cu_n = e.n; cu_lo = e.lo; cu_nsub = (e.n + SUB - 1) / SUB;
+                        found = true;
+                    }
                 }
-                c.r += step;
+                if (!found) break;
+                cu_c = (team + cu_row_n) & 1;
             }
         };
-        auto advance = [&](Cursor& c) {
-            if (c.r >= rows) return;
-            c.base += CHUNK;
-            if (c.base >= c.hi) { c.r += step; seek(c); }
+        struct Desc {  // what the later pipeline steps need to know about a sub-chunk
+            int gi;       // global sub-chunk index (-1: none)
+            int row_n;
+            bool last;    // the team's last sub-chunk of its row: deliver the rhs partial
+        };
+        auto describe = [&]() -> Desc {
+            if (cu_k >= nslots) return Desc{-1, 0, false};
+            return Desc{cu_gi0 + cu_c, cu_row_n, cu_c + 2 >= cu_nsub};
         };
         struct Raw { int idx; float d; };
         bool saw_negative = false;
-        auto load_raw = [&](const Cursor& c) {  // lane l < 8 of warp w: entry 8w + l of the chunk
+        auto load_raw = [&]() {  // lane l < 8 of warp w: entry 8w + l of the cursor's sub-chunk
             Raw rw{-1, 0.f};
-            if (c.r < rows && lane < 8) {
-                const int64_t e = c.base + gw * 8 + lane;
-                if (e < c.hi) { rw.d = __ldg(p.data + e); rw.idx = __ldg(p.indices + e); }
+            if (cu_k < nslots && lane < 8) {
+                const int off = cu_c * SUB + gw * 8 + lane;
+                if (off < cu_n) { rw.d = __ldg(p.data + cu_lo + off); rw.idx = __ldg(p.indices + cu_lo + off); }
             }
             return rw;
         };
-        float2* metaS = reinterpret_cast<float2*>(smem + OFF_META);
         auto issue = [&](const Raw& rw, int buf) {
+            const int tb = team * NSTG + buf;
             if (lane < 8) {
                 float sq = 0.f, dp1 = 0.f;
                 if (rw.idx >= 0) {
                     if (rw.d < 0.f) saw_negative = true;
-                    sq = sqrtf(fabsf(rw.d));
+                    sq = S * sqrtf(fabsf(rw.d));
                     dp1 = __fadd_rn(rw.d, 1.0f);
                 }
-                metaS[buf * CHUNK + gw * 8 + lane] = make_float2(sq, dp1);
+                const uint32_t ma = smem_base + OFF_META + tb * META_BYTES + (gw * 8 + lane) * 4;
+                sts1(ma, sq);
+                sts1(ma + SUB * 4, dp1);
             }
-            const uint32_t dst0 = smem_base + OFF_STG + buf * STG_BYTES + (gw * 8) * (F * 4) + lane * 16;
+            const uint32_t dst0 = smem_base + OFF_STG + tb * STG_BYTES + (gw * 8) * (F * 4) + lane * 16;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const int idx = __shfl_sync(0xffffffffu, rw.idx, jj);
                 const float* src = p.Y + (int64_t)(idx >= 0 ? idx : 0) * p.ldy + lane * 4;
                 cp_async16(dst0 + jj * (F * 4), src, idx >= 0 ? 16u : 0u);  // size 0 -> zero fill
             }
-            cp_async_arrive(bar_stg(buf));
+            cp_async_arrive(bar_stg(team, buf));
         };
-        Cursor c0{first, 0, 0};
-        seek(c0);
-        Cursor c1 = c0; advance(c1);
-        Cursor c2 = c1; advance(c2);
-        Cursor c3 = c2; advance(c3);
-        issue(load_raw(c0), 0);
-        issue(load_raw(c1), 1);
-        Raw r2 = load_raw(c2);
-        uint32_t chunk_n = 0, row_n = 0;
+        advance(true);
+        Desc d0 = describe();
+        issue(load_raw(), 0);
+        advance(false);
+        Desc d1 = describe();
+        issue(load_raw(), 1);
+        advance(false);
+        Desc d2 = describe();
+        Raw r2 = load_raw();
+        advance(false);
+        uint32_t j = 0;
         double bacc = 0.0;
-        const bool prof = PROF && blockIdx.x == 0 && m == 0;
-        long long t_empty = 0, t_bempty = 0, t_stg = 0, t_acc = 0, t_start = prof ? clock64() : 0, tt = 0;
-        long long t_issue = 0, t_xform = 0, t_bar = 0, t_mma = 0, t2 = 0;
-        while (c0.r < rows) {
+        const bool prof = PROF && blockIdx.x == 0 && m == 0 && team == 0;
+        long long t_empty = 0, t_bempty = 0, t_stg = 0, t_issue = 0, t_xform = 0, t_start = prof ? clock64() : 0, tt = 0, t2 = 0;
+        while (d0.gi >= 0) {
             if (prof) t2 = clock64();
-            // buffer (i+2)%3 was read by every gather thread during iteration i-1: barrier before refilling it
-            asm volatile("bar.sync %0, %1;" ::"n"(1 + NGROUP), "n"(GATHER_THREADS) : "memory");
-            issue(r2, (chunk_n + 2) % NSTG);   // chunk i+2
-            r2 = load_raw(c3);                 // chunk i+3, first touched next iteration
-            const int s = chunk_n % NSTAGE, sb = chunk_n % NSTG;
+            // buffer (j+2)%3 was read by every thread of the team during iteration j-1: barrier before refilling it
+            named_bar(1 + NGROUP + team, TEAM);
+            const Desc d3 = describe();
+            issue(r2, (j + 2) % NSTG);   // sub-chunk j+2
+            r2 = load_raw();             // sub-chunk j+3, first touched next iteration
+            advance(false);
+            const int s = d0.gi % NSTAGE, sb = j % NSTG;
             if (prof) { tt = clock64(); t_issue += tt - t2; }
-            mbar_wait(bar_stg(sb), (chunk_n / NSTG) & 1u);
-            if (prof) { t_stg += clock64() - tt; tt = clock64(); }
-            mbar_wait(bar_empty(s), ((chunk_n / NSTAGE) & 1u) ^ 1u);
-            if (prof) { t2 = clock64(); t_empty += t2 - tt; }
-            const float* stg = reinterpret_cast<const float*>(smem + OFF_STG + sb * STG_BYTES) + m;
-            const float2* mt = metaS + sb * CHUNK;
-            uint8_t* tile_h = smem + OFF_STAGES + s * STAGE_BYTES + m * 128;
-            uint8_t* tile_l = tile_h + TILE_BYTES;
+            mbar_wait(bar_stg(team, sb), (j / NSTG) & 1u);
+            if (prof) { t2 = clock64(); t_stg += t2 - tt; }
+            mbar_wait(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
+            if (prof) { tt = clock64(); t_empty += tt - t2; }
+            const uint32_t stg = smem_base + OFF_STG + (team * NSTG + sb) * STG_BYTES + m * 4;
+            const uint32_t mt = smem_base + OFF_META + (team * NSTG + sb) * META_BYTES;
+            const uint32_t tile_h = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + m * 128;
+            const int half = s & 1;
             float part = 0.f;
 #pragma unroll
-            for (int g4 = 0; g4 < CHUNK / 4; ++g4) {
-                float zh[4], zl[4];
+            for (int c = 0; c < SUB / 8; ++c) {   // one 16-byte chunk = 8 entries of this feature
+                const float4 sa = lds4(mt + c * 32), sb4 = lds4(mt + c * 32 + 16);
+                const float4 da = lds4(mt + SUB * 4 + c * 32), db = lds4(mt + SUB * 4 + c * 32 + 16);
+                const float sq[8] = {sa.x, sa.y, sa.z, sa.w, sb4.x, sb4.y, sb4.z, sb4.w};
+                const float dp[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                uint32_t hh[4], ll[4];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = g4 * 4 + jj;
-                    const float v = stg[j * F];
-                    const float2 sc = mt[j];
-                    const float z = sc.x * v;
-                    zh[jj] = tf32_round(z);
-                    zl[jj] = tf32_round(z - zh[jj]);
-                    part = fmaf(sc.y, v, part);
+                for (int e = 0; e < 4; ++e) {
+                    const float v0 = lds1(stg + (c * 8 + 2 * e) * (F * 4));
+                    const float v1 = lds1(stg + (c * 8 + 2 * e + 1) * (F * 4));
+                    const float z0 = sq[2 * e] * v0, z1 = sq[2 * e + 1] * v1;
+                    part = fmaf(dp[2 * e], v0, part);
+                    part = fmaf(dp[2 * e + 1], v1, part);
+                    const __half2 h = __floats2half2_rn(z0, z1);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
+                    hh[e] = h2_bits(h);
+                    ll[e] = h2_bits(l);
                 }
-                const int sw = (g4 ^ (m & 7)) << 4;  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-                *reinterpret_cast<float4*>(tile_h + sw) = make_float4(zh[0], zh[1], zh[2], zh[3]);
-                *reinterpret_cast<float4*>(tile_l + sw) = make_float4(zl[0], zl[1], zl[2], zl[3]);
+                const uint32_t sw = (uint32_t)(((half * 4 + c) ^ (m & 7)) << 4);  // 128B swizzle: chunk index XOR (row mod 8)
+                sts4u(tile_h + sw, hh[0], hh[1], hh[2], hh[3]);
+                sts4u(tile_h + TILE_BYTES + sw, ll[0], ll[1], ll[2], ll[3]);
             }
             bacc += (double)part;
-            if (prof) { tt = clock64(); t_xform += tt - t2; }
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full(s));
-            if (prof) { t2 = clock64(); t_bar += t2 - tt; }
-            const bool last_chunk = c0.base + CHUNK >= c0.hi;
-            const int g = row_n % NGROUP;
-            ++chunk_n;
-            if (last_chunk) {  // hand the rhs to the solver group that owns this row
-                const uint32_t bph = (row_n / NGROUP) & 1u;
-                if (prof) tt = clock64();
+            if (prof) { t2 = clock64(); t_xform += t2 - tt; }
+            if (d0.last) {  // hand the team's rhs partial to the solver group that owns this row
+                const int g = d0.row_n % NGROUP;
+                const uint32_t bph = ((uint32_t)d0.row_n / NGROUP) & 1u;
                 mbar_wait(bar_b_empty(g), bph ^ 1u);
-                if (prof) t_bempty += clock64() - tt;
-                bvec[g * F + m] = (float)bacc;
-                mbar_arrive(bar_b_full(g));
+                sts1(smem_base + OFF_BVEC + ((g * NTEAM + team) * F + m) * 4, (float)bacc);
+                mbar_arrive(bar_b_full(g, team));
                 bacc = 0.0;
-                ++row_n;
+                if (prof) t_bempty += clock64() - t2;
             }
-            c0 = c1; c1 = c2; c2 = c3;
-            advance(c3);
+            ++j;
+            d0 = d1; d1 = d2; d2 = d3;
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         if (saw_negative) atomicOr(flags, 1);
-        if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = chunk_n; p.prof[4] = row_n; p.prof[5] = t_stg; p.prof[6] = t_acc; p.prof[11] = t_issue; p.prof[12] = t_xform; p.prof[13] = t_bar; p.prof[14] = t_mma; }
+        if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = j; p.prof[5] = t_stg; p.prof[11] = t_issue; p.prof[12] = t_xform; }
     } else if (warp == MMA_WARP) {
         // =============================== GRAM MMA ISSUE ===============================
         if (lane == 0) {
-            uint32_t chunk_n = 0, row_n = 0;
+            uint32_t gi = 0, row_n = 0, ks = 0;
             const bool prof = PROF && blockIdx.x == 0;
-            long long t_full = 0, t_accempty = 0, t_start = prof ? clock64() : 0, tt = 0;
-            for (int64_t r = first; r < rows; r += step) {
-                const int64_t row = p.row_order ? p.row_order[r] : r;
-                if (row < 0) continue;
-                const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-                if (lo == hi) continue;
+            long long t_full = 0, t_accempty = 0, t_thr = 0, t_start = prof ? clock64() : 0, tt = 0;
+            RowEnt nxt = ent_at(0);
+            for (int k = 0; k < nslots; ++k) {
+                const RowEnt e = nxt;
+                nxt = ent_at(k + 1);
+                if (e.n <= 0) continue;
                 const int g = row_n % NGROUP;
                 const uint32_t aph = (row_n / NGROUP) & 1u;
                 if (prof) tt = clock64();
@@ -402,31 +489,36 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
                 uint32_t accumulate = 0;
-                for (int64_t base = lo; base < hi; base += CHUNK, ++chunk_n) {
-                    const int s = chunk_n % NSTAGE;
-                    const uint32_t ph = (chunk_n / NSTAGE) & 1u;
+                for (int base = 0; base < e.n; base += SUB, ++gi) {
+                    const int s = gi % NSTAGE;
                     if (prof) tt = clock64();
-                    mbar_wait(bar_full(s), ph);
+                    mbar_wait(bar_full(s), (gi / NSTAGE) & 1u);
                     if (prof) t_full += clock64() - tt;
                     tc_fence_after();
-                    const int kc = (int)((hi - base) < CHUNK ? (hi - base) : CHUNK);
-                    const int nk = (kc + 7) >> 3;
-                    const uint32_t tile = smem_base + OFF_STAGES + s * STAGE_BYTES;
+                    const int kc = (e.n - base) < SUB ? (e.n - base) : SUB;
+                    const int nk = (kc + 15) >> 4;
+                    const uint32_t tile = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + (s & 1) * 64;
                     const uint64_t dh = umma_desc(tile), dl = umma_desc(tile + TILE_BYTES);
-                    for (int k = 0; k < nk; ++k) {
-                        // advance 8 fp32 = 32 B along K inside the 128-B swizzle row
-                        const uint64_t hk = dh + (uint64_t)(k * 2), lk = dl + (uint64_t)(k * 2);
-                        umma_tf32(d_tmem, hk, hk, IDESC_TF32_M128_N128, accumulate);  // zh zh^T
-                        umma_tf32(d_tmem, hk, lk, IDESC_TF32_M128_N128, 1u);          // zh zl^T
-                        umma_tf32(d_tmem, lk, hk, IDESC_TF32_M128_N128, 1u);          // zl zh^T
+                    for (int kk = 0; kk < nk; ++kk, ++ks) {
+                        if (ks >= 2) {  // at most two K-steps queued ahead of the solvers' updates
+                            if (prof) tt = clock64();
+                            mbar_wait(bar_thr(ks & 1), ((ks >> 1) - 1) & 1u);
+                            if (prof) t_thr += clock64() - tt;
+                        }
+                        // advance 16 fp16 = 32 B along K inside the 128-B swizzle row
+                        const uint64_t hk = dh + (uint64_t)(kk * 2), lk = dl + (uint64_t)(kk * 2);
+                        umma_f16(d_tmem, hk, hk, IDESC_F16_M128_N128, accumulate);  // zh zh^T
+                        umma_f16(d_tmem, hk, lk, IDESC_F16_M128_N128, 1u);          // zh zl^T
+                        umma_f16(d_tmem, lk, hk, IDESC_F16_M128_N128, 1u);          // zl zh^T
                         accumulate = 1;
+                        tc_commit(bar_thr(ks & 1));
                     }
                     tc_commit(bar_empty(s));
                 }
                 tc_commit(bar_acc_full(g));
                 ++row_n;
             }
-            if (prof) { p.prof[8] = clock64() - t_start; p.prof[9] = t_full; p.prof[10] = t_accempty; }
+            if (prof) { p.prof[8] = clock64() - t_start; p.prof[9] = t_full; p.prof[10] = t_accempty; p.prof[13] = t_thr; }
         }
     } else {
         // =============================== SOLVE (matrix resident in TMEM) ===============================
@@ -443,29 +535,34 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
         const float* Grow = p.G + t * F;
-        uint32_t row_n = 0, my_rows = 0, panel_n = 0;
+        const float inv_s2 = 1.0f / (S * S);  // exact: S is a power of two
+        uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
-        long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0;
-        for (int64_t r = first; r < rows; r += step) {
-            const int64_t row = p.row_order ? p.row_order[r] : r;
-            if (row < 0) continue;
-            const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-            float* xout = p.X + row * p.ldx;
-            if (lo == hi) {  // wmf_model.py:223-225
-                if (g == 0) xout[t] = 0.0f;
-                continue;
-            }
-            const bool mine = (int)(row_n % NGROUP) == g;
-            ++row_n;
-            if (!mine) continue;
-            const uint32_t ph = my_rows & 1u;
+        long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0, my_rows = 0;
+        RowEnt nxt = ent_at(0);
+        for (int k = 0; k < nslots; ++k) {
+            const RowEnt e = nxt;
+            nxt = ent_at(k + 1);
+            if (e.n <= 0) continue;
+            const uint32_t rn = row_n++;
+            if ((int)(rn % NGROUP) != g) continue;
             ++my_rows;
+            float* xout = p.X + (int64_t)e.row * p.ldx;
             if (prof) tt = clock64();
-            mbar_wait(bar_b_full(g), ph);
-            float bt = lds1(smem_base + OFF_BVEC + (g * F + t) * 4);
+            // rhs partials: the team that owns sub-chunk 0 always delivers, the other one if the row has two or more
+            const int t0 = rn & 1;
+            float bt;
+            {
+                float bA = 0.0f, bB = 0.0f;  // team 0, team 1
+                const bool both = e.n > SUB;
+                if (t0 == 0 || both) { mbar_wait(bar_b_full(g, 0), cnt_b0 & 1u); ++cnt_b0; bA = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 0) * F + t) * 4); }
+                if (t0 == 1 || both) { mbar_wait(bar_b_full(g, 1), cnt_b1 & 1u); ++cnt_b1; bB = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 1) * F + t) * 4); }
+                bt = bA + bB;
+            }
+            float dbg_val = bt;
             mbar_arrive(bar_b_empty(g));
-            mbar_wait(bar_acc_full(g), ph);
+            mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
             tc_fence_after();
             if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
 #pragma unroll 1
@@ -485,10 +582,11 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                     tc_fence_before();
                     mbar_arrive(bar_acc_empty(g));
                 }
-                a[0] = __fadd_rn(a[0], g0.x); a[1] = __fadd_rn(a[1], g0.y); a[2] = __fadd_rn(a[2], g0.z);
-                a[3] = __fadd_rn(a[3], g0.w); a[4] = __fadd_rn(a[4], g1.x); a[5] = __fadd_rn(a[5], g1.y);
-                a[6] = __fadd_rn(a[6], g1.z); a[7] = __fadd_rn(a[7], g1.w);
+                a[0] = fmaf(a[0], inv_s2, g0.x); a[1] = fmaf(a[1], inv_s2, g0.y); a[2] = fmaf(a[2], inv_s2, g0.z);
+                a[3] = fmaf(a[3], inv_s2, g0.w); a[4] = fmaf(a[4], inv_s2, g1.x); a[5] = fmaf(a[5], inv_s2, g1.y);
+                a[6] = fmaf(a[6], inv_s2, g1.z); a[7] = fmaf(a[7], inv_s2, g1.w);
                 if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
+                if (p.KC >= 2 && c0 == ((p.KC - 2) >> 3) * 8) dbg_val = a[(p.KC - 2) & 7];  // debug: column KC-2 of A
                 const int rel = t - c0;
                 const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
                 if (q == (c0 >> 5)) {
@@ -537,26 +635,26 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                     }
                     if (prof) { t4 = clock64(); ph_own += t4 - t3; }
                 }
-                group_bar(bar_id);
+                named_bar(bar_id, GROUP);
                 // ---- every row outside the block: P = a N^T, rhs -= P zb; the block's own rows are pivots (P = 0) ----
                 float P[NB];
                 {
                     const bool pivot = rel >= 0 && rel < NB;
 #pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        const float4 n0 = lds4(nd + j * 32);
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const float4 n0 = lds4(nd + jj * 32);
                         float v = a[0] * n0.x;
-                        if (j >= 1) v = fmaf(a[1], n0.y, v);
-                        if (j >= 2) v = fmaf(a[2], n0.z, v);
-                        if (j >= 3) v = fmaf(a[3], n0.w, v);
-                        if (j >= 4) {
-                            const float4 n1 = lds4(nd + j * 32 + 16);
+                        if (jj >= 1) v = fmaf(a[1], n0.y, v);
+                        if (jj >= 2) v = fmaf(a[2], n0.z, v);
+                        if (jj >= 3) v = fmaf(a[3], n0.w, v);
+                        if (jj >= 4) {
+                            const float4 n1 = lds4(nd + jj * 32 + 16);
                             v = fmaf(a[4], n1.x, v);
-                            if (j >= 5) v = fmaf(a[5], n1.y, v);
-                            if (j >= 6) v = fmaf(a[6], n1.z, v);
-                            if (j >= 7) v = fmaf(a[7], n1.w, v);
+                            if (jj >= 5) v = fmaf(a[5], n1.y, v);
+                            if (jj >= 6) v = fmaf(a[6], n1.z, v);
+                            if (jj >= 7) v = fmaf(a[7], n1.w, v);
                         }
-                        P[j] = pivot ? 0.0f : v;
+                        P[jj] = pivot ? 0.0f : v;
                     }
                     const float4 z0 = lds4(zd), z1 = lds4(zd + 16);
                     float u0 = P[0] * z0.x, u1 = P[1] * z0.y;  // two chains, fixed order
@@ -568,9 +666,10 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                 if (c0 + NB < F) {
                     float lh[NB], ll[NB];
 #pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        lh[j] = tf32_round(P[j]);
-                        ll[j] = tf32_round(P[j] - lh[j]);
+                    for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
+                        const float ps = P[jj] * S;
+                        lh[jj] = tf32_round(ps);
+                        ll[jj] = tf32_round(ps - lh[jj]);
                     }
                     const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
                     sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
@@ -580,7 +679,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                     fence_async_smem();
                     tc_fence_before();
                     if (prof) t3 = clock64();
-                    group_bar(bar_id);
+                    named_bar(bar_id, GROUP);
                     if (t == 0) {
                         // S[:, j] -= P P[j]^T for the live columns j >= c0 + 8 (all 128 rows: Gauss-Jordan)
                         tc_fence_after();
@@ -599,7 +698,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
             if (prof) { t_fact += clock64() - tt; tt = clock64(); }
             // ---- the system is block diagonal now: x_blk = (L L^T)^-1 b_blk = N^T (N b_blk) ----
             sts1(bfin + t * 4, bt);
-            group_bar(bar_id);
+            named_bar(bar_id, GROUP);
             {
                 const int r8 = t & 7;
                 const uint32_t nb = Nst + (t >> 3) * 256, bq = bfin + (t >> 3) * 32;
@@ -607,20 +706,20 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
                 const float bb[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float xt = 0.0f;
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const float4 n0 = lds4(nb + j * 32), n1 = lds4(nb + j * 32 + 16);
+                for (int jj = 0; jj < NB; ++jj) {
+                    const float4 n0 = lds4(nb + jj * 32), n1 = lds4(nb + jj * 32 + 16);
                     const float nr[NB] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
                     float y = 0.0f;
 #pragma unroll
-                    for (int k = 0; k <= j; ++k) y = fmaf(nr[k], bb[k], y);
-                    float nsel = 0.0f;  // N[j][r8] (zero above the diagonal)
+                    for (int kk = 0; kk <= jj; ++kk) y = fmaf(nr[kk], bb[kk], y);
+                    float nsel = 0.0f;  // N[jj][r8] (zero above the diagonal)
 #pragma unroll
-                    for (int k = 0; k <= j; ++k) nsel = (k == r8) ? nr[k] : nsel;
+                    for (int kk = 0; kk <= jj; ++kk) nsel = (kk == r8) ? nr[kk] : nsel;
                     xt = fmaf(nsel, y, xt);
                 }
-                xout[t] = xt;
+                xout[t] = p.KC ? dbg_val : xt;
             }
-            group_bar(bar_id);  // Nst / bfin are rewritten by the next row
+            named_bar(bar_id, GROUP);  // Nst / bfin are rewritten by the next row
             if (prof) t_back += clock64() - tt;
         }
         if (prof) {
@@ -640,27 +739,45 @@ __global__ void __launch_bounds__(THREADS, 1) als_half_step_tc_kernel(HalfStepPa
 
 bool tc_half_step_supported(int f, int bias) { return f == tc::F && !bias; }
 
-size_t tc_half_step_workspace_bytes(int64_t, int f, int) {  // header + profile slots (f = 128 needs no SIMT slab)
+// header + profile slots + one 16-byte row-table entry per schedule slot (f = 128 needs no SIMT slab).
+// The public query only knows `rows`: schedules of up to 2*rows + 4096 slots fit.
+size_t tc_half_step_workspace_bytes(int64_t rows, int f, int) {
     const size_t a = simt_half_step_workspace_bytes(f);
-    return a > 1024 ? a : 1024;
+    const size_t b = WS_ROWTAB + sizeof(RowEnt) * (size_t)(2 * rows + 4096);
+    return a > b ? a : b;
 }
 
 int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st) {
-    const size_t need = tc_half_step_workspace_bytes(in.rows, in.f, in.bias);
-    if (ws == nullptr || ws_bytes < need) {
-        set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu", ws_bytes, need);
+    const size_t need = WS_ROWTAB + sizeof(RowEnt) * (size_t)in.sched_len;
+    if (ws == nullptr || ws_bytes < need || ws_bytes < simt_half_step_workspace_bytes(in.f)) {
+        set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu (schedule of %lld slots)", ws_bytes, need,
+                  (long long)in.sched_len);
         return WMF_ERR_WORKSPACE;
     }
-    WMF_CUDA(cudaMemsetAsync(ws, 0, 1024, st));
-    int* flags = reinterpret_cast<int*>(ws) + 1;  // [0] = SIMT row counter, [1] = redo flags
-    WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    WMF_CUDA(cudaMemsetAsync(ws, 0, WS_ROWTAB, st));
+    char* base = reinterpret_cast<char*>(ws);
+    int* flags = reinterpret_cast<int*>(base) + 1;  // [0] = SIMT row counter, [1] = redo flags
+    uint32_t* maxes = reinterpret_cast<uint32_t*>(base) + 2;
+    RowEnt* tab = reinterpret_cast<RowEnt*>(base + WS_ROWTAB);
+    static bool attr_set = false;
+    if (!attr_set) {
+        WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
     HalfStepParams p = in;
-    p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 256) : nullptr;
-    int grid = sm_count();
-    if ((int64_t)grid > in.rows) grid = (int)in.rows;
-    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, flags);
-    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, flags);
+    p.KC = getenv("WMF_TC_DEBUG") ? atoi(getenv("WMF_TC_DEBUG")) : 0;  // debug: 1 = output the rhs, 2+c = output column c of A
+    p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
+    const int sms = sm_count();
+    tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 255) / 256), 256, 0, st>>>(p, tab);
+    WMF_LAUNCH_CHECK("tc_prep_rows_kernel");
+    tc_maxima_kernel<<<sms * 4, 256, 0, st>>>(p, maxes);
+    WMF_LAUNCH_CHECK("tc_maxima_kernel");
+    int grid = sms;
+    if ((int64_t)grid > in.sched_len) grid = (int)in.sched_len;
+    const float* hdr = reinterpret_cast<const float*>(base);
+    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, hdr, flags);
+    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, hdr, flags);
     WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
     // fix-up: runs the FP32/LU kernel over the whole half-step only if a flag was raised
     HalfStepParams fix = in;
