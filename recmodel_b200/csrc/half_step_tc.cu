@@ -103,16 +103,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of
+// re-polling every ~50 cycles (polling was 30 % of all issued instructions, ncu r01b)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
+        "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -534,8 +536,8 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * F);
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
-        const float* Grow = p.G + t * F;
-        const float inv_s2 = 1.0f / (S * S);  // exact: S is a power of two
+        const float* Gcol = p.G + t;  // G is symmetric: G[t][c] = G[c][t], and column t is coalesced across the warp
+        const float inv_s = 1.0f / S, inv_s2 = inv_s * inv_s;  // exact: S is a power of two
         uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
@@ -567,8 +569,9 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
 #pragma unroll 1
             for (int c0 = 0; c0 < F; c0 += NB) {
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(Grow + c0));
-                const float4 g1 = __ldg(reinterpret_cast<const float4*>(Grow + c0 + 4));
+                float gg[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + (c0 + i) * F);
                 if (prof) t3 = clock64();
                 if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
                     mbar_wait(bar_panel(g), panel_n & 1u);
@@ -582,9 +585,8 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                     tc_fence_before();
                     mbar_arrive(bar_acc_empty(g));
                 }
-                a[0] = fmaf(a[0], inv_s2, g0.x); a[1] = fmaf(a[1], inv_s2, g0.y); a[2] = fmaf(a[2], inv_s2, g0.z);
-                a[3] = fmaf(a[3], inv_s2, g0.w); a[4] = fmaf(a[4], inv_s2, g1.x); a[5] = fmaf(a[5], inv_s2, g1.y);
-                a[6] = fmaf(a[6], inv_s2, g1.z); a[7] = fmaf(a[7], inv_s2, g1.w);
+#pragma unroll
+                for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, gg[i]);
                 if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
                 if (p.KC >= 2 && c0 == ((p.KC - 2) >> 3) * 8) dbg_val = a[(p.KC - 2) & 7];  // debug: column KC-2 of A
                 const int rel = t - c0;
@@ -620,26 +622,26 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                     }
                     Factor8 fo;
                     const bool ok = factor8(d, bb, fo);
-                    if (lane == 0) {
+                    if (lane == 0) {  // published scaled: S N and zb / S, so P comes out as S P (the MMA operand) for free
 #pragma unroll
                         for (int i = 0; i < NB; ++i) {
-                            sts4(nd + i * 32, fo.n[TRI(i, 0)], i >= 1 ? fo.n[TRI(i, 1)] : 0.f, i >= 2 ? fo.n[TRI(i, 2)] : 0.f,
-                                 i >= 3 ? fo.n[TRI(i, 3)] : 0.f);
+                            sts4(nd + i * 32, S * fo.n[TRI(i, 0)], i >= 1 ? S * fo.n[TRI(i, 1)] : 0.f,
+                                 i >= 2 ? S * fo.n[TRI(i, 2)] : 0.f, i >= 3 ? S * fo.n[TRI(i, 3)] : 0.f);
                             if (i >= 4)
-                                sts4(nd + i * 32 + 16, fo.n[TRI(i, 4)], i >= 5 ? fo.n[TRI(i, 5)] : 0.f,
-                                     i >= 6 ? fo.n[TRI(i, 6)] : 0.f, i >= 7 ? fo.n[TRI(i, 7)] : 0.f);
+                                sts4(nd + i * 32 + 16, S * fo.n[TRI(i, 4)], i >= 5 ? S * fo.n[TRI(i, 5)] : 0.f,
+                                     i >= 6 ? S * fo.n[TRI(i, 6)] : 0.f, i >= 7 ? S * fo.n[TRI(i, 7)] : 0.f);
                         }
-                        sts4(zd, fo.zb[0], fo.zb[1], fo.zb[2], fo.zb[3]);
-                        sts4(zd + 16, fo.zb[4], fo.zb[5], fo.zb[6], fo.zb[7]);
+                        sts4(zd, inv_s * fo.zb[0], inv_s * fo.zb[1], inv_s * fo.zb[2], inv_s * fo.zb[3]);
+                        sts4(zd + 16, inv_s * fo.zb[4], inv_s * fo.zb[5], inv_s * fo.zb[6], inv_s * fo.zb[7]);
                         if (!ok) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
                     }
                     if (prof) { t4 = clock64(); ph_own += t4 - t3; }
                 }
                 named_bar(bar_id, GROUP);
-                // ---- every row outside the block: P = a N^T, rhs -= P zb; the block's own rows are pivots (P = 0) ----
+                // ---- every row outside the block: P = a (S N)^T = S a N^T, rhs -= P (zb / S); the block's own rows
+                // are pivots (P = 0) ----
                 float P[NB];
                 {
-                    const bool pivot = rel >= 0 && rel < NB;
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
                         const float4 n0 = lds4(nd + jj * 32);
@@ -654,7 +656,12 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                             if (jj >= 6) v = fmaf(a[6], n1.z, v);
                             if (jj >= 7) v = fmaf(a[7], n1.w, v);
                         }
-                        P[jj] = pivot ? 0.0f : v;
+                        P[jj] = v;
+                    }
+                    if (q == (c0 >> 5)) {  // only the owner warp holds pivot rows
+                        const bool pivot = rel >= 0 && rel < NB;
+#pragma unroll
+                        for (int jj = 0; jj < NB; ++jj) P[jj] = pivot ? 0.0f : P[jj];
                     }
                     const float4 z0 = lds4(zd), z1 = lds4(zd + 16);
                     float u0 = P[0] * z0.x, u1 = P[1] * z0.y;  // two chains, fixed order
@@ -667,9 +674,8 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                     float lh[NB], ll[NB];
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
-                        const float ps = P[jj] * S;
-                        lh[jj] = tf32_round(ps);
-                        ll[jj] = tf32_round(ps - lh[jj]);
+                        lh[jj] = tf32_round(P[jj]);
+                        ll[jj] = P[jj] - lh[jj];  // exact; the tensor core reads its top 19 bits (error 2^-23 of P)
                     }
                     const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
                     sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
@@ -717,7 +723,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                     for (int kk = 0; kk <= jj; ++kk) nsel = (kk == r8) ? nr[kk] : nsel;
                     xt = fmaf(nsel, y, xt);
                 }
-                xout[t] = p.KC ? dbg_val : xt;
+                xout[t] = p.KC ? dbg_val : xt * inv_s2;  // N was stored as S N
             }
             named_bar(bar_id, GROUP);  // Nst / bfin are rewritten by the next row
             if (prof) t_back += clock64() - tt;
