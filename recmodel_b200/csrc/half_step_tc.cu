@@ -70,8 +70,9 @@ constexpr int G_OFF_TILEL = G_OFF_TILEH + PANEL_TILE_BYTES;
 constexpr int G_OFF_NINV = G_OFF_TILEL + PANEL_TILE_BYTES;          // 16 blocks x (8 x 8) floats: N = L^-1 per pivot block
 constexpr int G_OFF_ZB = G_OFF_NINV + (F / NB) * NB * NB * 4;       // 16 x 8 floats: N b_blk
 constexpr int G_OFF_DBLK = G_OFF_ZB + (F / NB) * NB * 4;            // 8 x 8 pivot block + 8 rhs
-constexpr int G_OFF_BFIN = G_OFF_DBLK + (NB * NB + 2 * NB) * 4;     // 128 floats: final rhs
-constexpr int GROUP_BYTES = ((G_OFF_BFIN + F * 4 + 127) / 128) * 128;
+constexpr int G_OFF_BFIN = G_OFF_DBLK + (NB * NB + 4 * NB) * 4;     // 128 floats: final rhs
+constexpr int G_OFF_PNX = G_OFF_BFIN + F * 4;                       // 8 x 8 floats: P rows of the next pivot block
+constexpr int GROUP_BYTES = ((G_OFF_PNX + NB * NB * 4 + 127) / 128) * 128;
 
 // shared memory carve-up (bytes from a 1024-aligned base)
 constexpr int OFF_STAGES = 0;                                        // NSTAGE/2 tile pairs
@@ -202,6 +203,9 @@ __device__ __forceinline__ void sts1(uint32_t a, float x) {
 }
 __device__ __forceinline__ void named_bar(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {  // non-blocking arrival
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -413,7 +417,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         while (d0.gi >= 0) {
             if (prof) t2 = clock64();
             // buffer (j+2)%3 was read by every thread of the team during iteration j-1: barrier before refilling it
-            named_bar(1 + NGROUP + team, TEAM);
+            named_bar(1 + 2 * NGROUP + team, TEAM);
             const Desc d3 = describe();
             issue(r2, (j + 2) % NSTG);   // sub-chunk j+2
             r2 = load_raw();             // sub-chunk j+3, first touched next iteration
@@ -532,7 +536,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         const int bar_id = 1 + g;
         const uint32_t gs = smem_base + OFF_GROUPS + g * GROUP_BYTES;
         const uint32_t tileH = gs + G_OFF_TILEH, tileL = gs + G_OFF_TILEL;
-        const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN;
+        const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN, Pnx = gs + G_OFF_PNX;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * F);
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
@@ -540,6 +544,8 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         const float inv_s = 1.0f / S, inv_s2 = inv_s * inv_s;  // exact: S is a power of two
         uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
+        long long* trace = PROF ? reinterpret_cast<long long*>(const_cast<RowEnt*>(rowtab) + p.sched_len) : nullptr;
+        bool tr = false;  // lane 0 of every warp of group 0 / CTA 0 stamps one row
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
         long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0, my_rows = 0;
         RowEnt nxt = ent_at(0);
@@ -550,6 +556,8 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             const uint32_t rn = row_n++;
             if ((int)(rn % NGROUP) != g) continue;
             ++my_rows;
+            tr = PROF && blockIdx.x == 0 && g == 0 && lane == 0 && my_rows == 60;
+#define STAMP(i) do { if (PROF && tr) trace[((q * 16 + (c0 >> 3)) * 8) + (i)] = clock64(); } while (0)
             float* xout = p.X + (int64_t)e.row * p.ldx;
             if (prof) tt = clock64();
             // rhs partials: the team that owns sub-chunk 0 always delivers, the other one if the row has two or more
@@ -567,30 +575,31 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
             tc_fence_after();
             if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
-#pragma unroll 1
-            for (int c0 = 0; c0 < F; c0 += NB) {
+            // The columns of the current step live in registers, fully updated: they are read from TMEM one
+            // step ahead (when the rank-8 update of step k-1 has landed) and step k is applied to them in
+            // registers, so the tensor-core round trip of step k overlaps the pivot chain of step k+1.
+            float a[NB];
+            {
                 float gg[NB];
 #pragma unroll
-                for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + (c0 + i) * F);
-                if (prof) t3 = clock64();
-                if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
-                    mbar_wait(bar_panel(g), panel_n & 1u);
-                    ++panel_n;
-                    tc_fence_after();
-                }
-                if (prof) { t4 = clock64(); ph_wait += t4 - t3; }
-                float a[NB];
-                tmem_ld8(t_row + c0, a);
-                if (c0 + NB == F) {  // last read of the accumulator: the Gram of this group's next row may start
-                    tc_fence_before();
-                    mbar_arrive(bar_acc_empty(g));
-                }
+                for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + i * F);
+                tmem_ld8(t_row, a);
 #pragma unroll
                 for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, gg[i]);
-                if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
-                if (p.KC >= 2 && c0 == ((p.KC - 2) >> 3) * 8) dbg_val = a[(p.KC - 2) & 7];  // debug: column KC-2 of A
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < F; c0 += NB) {
                 const int rel = t - c0;
+                const bool more = c0 + NB < F;          // another step follows
+                const bool update = c0 + 2 * NB < F;    // columns beyond the next step exist: rank-8 update on the tensor core
                 const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
+                float gg[NB];  // G entries of the next step's columns (in flight during the pivot chain)
+                if (more) {
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + (c0 + NB + i) * F);
+                }
+                STAMP(0);
+                if (prof) t3 = clock64();
                 if (q == (c0 >> 5)) {
                     // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
                     if (rel >= 0 && rel < NB) {
@@ -637,7 +646,9 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                     }
                     if (prof) { t4 = clock64(); ph_own += t4 - t3; }
                 }
+                STAMP(1);
                 named_bar(bar_id, GROUP);
+                STAMP(2);
                 // ---- every row outside the block: P = a (S N)^T = S a N^T, rhs -= P (zb / S); the block's own rows
                 // are pivots (P = 0) ----
                 float P[NB];
@@ -670,35 +681,91 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                     u0 = fmaf(P[6], z1.z, u0); u1 = fmaf(P[7], z1.w, u1);
                     bt -= u0 + u1;
                 }
-                if (c0 + NB < F) {
-                    float lh[NB], ll[NB];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
-                        lh[jj] = tf32_round(P[jj]);
-                        ll[jj] = P[jj] - lh[jj];  // exact; the tensor core reads its top 19 bits (error 2^-23 of P)
-                    }
-                    const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
-                    sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
-                    sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
-                    sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
-                    sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
-                    fence_async_smem();
-                    tc_fence_before();
+                STAMP(3);
+                if (more) {
+                    // next step's columns: steps < k are in TMEM once the previous update has landed; step k is applied below
                     if (prof) t3 = clock64();
-                    named_bar(bar_id, GROUP);
-                    if (t == 0) {
-                        // S[:, j] -= P P[j]^T for the live columns j >= c0 + 8 (all 128 rows: Gauss-Jordan)
+                    if (c0 > 0) {
+                        mbar_wait(bar_panel(g), panel_n & 1u);
+                        ++panel_n;
                         tc_fence_after();
-                        if (prof) { t4 = clock64(); ph_p += t4 - t3; }
-                        const uint32_t start = (uint32_t)((c0 + NB) >> 4) << 4;
-                        const uint32_t idesc = IDESC_TF32_NEG_M128 | (((F - start) >> 3) << 17);
-                        const uint64_t bH = descH + (uint64_t)(start * 2), bL = descL + (uint64_t)(start * 2);
-                        umma_tf32(d_tmem + start, descH, bH, idesc, 1u);
-                        umma_tf32(d_tmem + start, descH, bL, idesc, 1u);
-                        umma_tf32(d_tmem + start, descL, bH, idesc, 1u);
-                        tc_commit(bar_panel(g));
-                        if (prof) ph_issue += clock64() - t4;
                     }
+                    if (prof) { t4 = clock64(); ph_wait += t4 - t3; }
+                    STAMP(4);
+                    float an[NB];
+                    tmem_ld8(t_row + c0 + NB, an);
+                    if (!update) {  // last read of the accumulator: the Gram of this group's next row may start
+                        tc_fence_before();
+                        mbar_arrive(bar_acc_empty(g));
+                    }
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) an[i] = fmaf(an[i], inv_s2, gg[i]);
+                    if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
+                    STAMP(5);
+                    // The warp that owns the next pivot block is the critical path: it brings its columns up to
+                    // date first (its own lanes hold the 8 rows of P it needs), only arrives at the hand-over
+                    // barrier and goes straight on to the next Cholesky; the other warps publish their tile,
+                    // one of them issues the rank-8 update, and they update their registers afterwards.
+                    const int nq = (c0 + NB) >> 5;
+                    auto publish_tile = [&]() {
+                        float lh[NB], ll[NB];
+#pragma unroll
+                        for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
+                            lh[jj] = tf32_round(P[jj]);
+                            ll[jj] = P[jj] - lh[jj];  // exact; the tensor core reads its top 19 bits (error 2^-23 of P)
+                        }
+                        const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+                        sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
+                        sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
+                        sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
+                        sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
+                        fence_async_smem();
+                    };
+                    auto update_regs = [&]() {  // a_next -= P P_next^T
+#pragma unroll
+                        for (int jj = 0; jj < NB; ++jj) {
+                            const float4 n0 = lds4(Pnx + jj * 32), n1 = lds4(Pnx + jj * 32 + 16);
+                            float u0 = P[0] * n0.x, u1 = P[1] * n0.y;
+                            u0 = fmaf(P[2], n0.z, u0); u1 = fmaf(P[3], n0.w, u1);
+                            u0 = fmaf(P[4], n1.x, u0); u1 = fmaf(P[5], n1.y, u1);
+                            u0 = fmaf(P[6], n1.z, u0); u1 = fmaf(P[7], n1.w, u1);
+                            a[jj] = an[jj] - (u0 + u1);
+                        }
+                    };
+                    if (q == nq) {
+                        // rows of the next pivot block publish their P (times 1/S^2: the product with S P is then unscaled)
+                        if (rel >= NB && rel < 2 * NB) {
+                            sts4(Pnx + (rel - NB) * 32, P[0] * inv_s2, P[1] * inv_s2, P[2] * inv_s2, P[3] * inv_s2);
+                            sts4(Pnx + (rel - NB) * 32 + 16, P[4] * inv_s2, P[5] * inv_s2, P[6] * inv_s2, P[7] * inv_s2);
+                        }
+                        __syncwarp();
+                        update_regs();
+                        if (update) publish_tile();
+                        tc_fence_before();
+                        named_bar_arrive(bar_id + NGROUP, GROUP);
+                        STAMP(6);
+                    } else {
+                        if (update) publish_tile();
+                        tc_fence_before();
+                        if (prof) t3 = clock64();
+                        named_bar(bar_id + NGROUP, GROUP);
+                        STAMP(6);
+                        if (update && q == ((nq + 2) & 3) && lane == 0) {
+                            // S[:, j] -= P P[j]^T for the columns beyond the next step (all 128 rows: Gauss-Jordan)
+                            tc_fence_after();
+                            if (prof) { t4 = clock64(); ph_p += t4 - t3; }
+                            const uint32_t start = (uint32_t)((c0 + 2 * NB) >> 4) << 4;
+                            const uint32_t idesc = IDESC_TF32_NEG_M128 | (((F - start) >> 3) << 17);
+                            const uint64_t bH = descH + (uint64_t)(start * 2), bL = descL + (uint64_t)(start * 2);
+                            umma_tf32(d_tmem + start, descH, bH, idesc, 1u);
+                            umma_tf32(d_tmem + start, descH, bL, idesc, 1u);
+                            umma_tf32(d_tmem + start, descL, bH, idesc, 1u);
+                            tc_commit(bar_panel(g));
+                            if (prof) ph_issue += clock64() - t4;
+                        }
+                        update_regs();
+                    }
+                    STAMP(7);
                 }
             }
             if (prof) { t_fact += clock64() - tt; tt = clock64(); }
