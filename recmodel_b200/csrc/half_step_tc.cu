@@ -70,7 +70,8 @@ constexpr int G_OFF_TILEL = G_OFF_TILEH + PANEL_TILE_BYTES;
 constexpr int G_OFF_NINV = G_OFF_TILEL + PANEL_TILE_BYTES;          // 16 blocks x (8 x 8) floats: N = L^-1 per pivot block
 constexpr int G_OFF_ZB = G_OFF_NINV + (F / NB) * NB * NB * 4;       // 16 x 8 floats: N b_blk
 constexpr int G_OFF_DBLK = G_OFF_ZB + (F / NB) * NB * 4;            // 8 x 8 pivot block + 8 rhs
-constexpr int G_OFF_BFIN = G_OFF_DBLK + (NB * NB + 4 * NB) * 4;     // 128 floats: final rhs
+constexpr int DBLK_BYTES = (NB * NB + 2 * NB) * 4;                   // 320: 8 x 8 block, 8 rhs, pad
+constexpr int G_OFF_BFIN = G_OFF_DBLK + 2 * DBLK_BYTES;     // 128 floats: final rhs
 constexpr int G_OFF_PNX = G_OFF_BFIN + F * 4;                       // 8 x 8 floats: P rows of the next pivot block
 constexpr int GROUP_BYTES = ((G_OFF_PNX + NB * NB * 4 + 127) / 128) * 128;
 
@@ -116,6 +117,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
         "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+// waits that are not on a critical path back off between polls (polling was ~27 % of all issued instructions)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -174,6 +189,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {  // results valid after tmem_ld_wait()
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -323,6 +344,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         return e;
     };
     const float S = gram_scale(hdr);
+    const uint32_t ngr = p.FP > 0 ? (uint32_t)p.FP : (uint32_t)NGROUP;  // experiment: active solver groups
 
     if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
         // =============================== GATHER ===============================
@@ -426,7 +448,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             if (prof) { tt = clock64(); t_issue += tt - t2; }
             mbar_wait(bar_stg(team, sb), (j / NSTG) & 1u);
             if (prof) { t2 = clock64(); t_stg += t2 - tt; }
-            mbar_wait(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
+            mbar_wait_relaxed(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
             if (prof) { tt = clock64(); t_empty += tt - t2; }
             const uint32_t stg = smem_base + OFF_STG + (team * NSTG + sb) * STG_BYTES + m * 4;
             const uint32_t mt = smem_base + OFF_META + (team * NSTG + sb) * META_BYTES;
@@ -462,9 +484,9 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             mbar_arrive(bar_full(s));
             if (prof) { t2 = clock64(); t_xform += t2 - tt; }
             if (d0.last) {  // hand the team's rhs partial to the solver group that owns this row
-                const int g = d0.row_n % NGROUP;
-                const uint32_t bph = ((uint32_t)d0.row_n / NGROUP) & 1u;
-                mbar_wait(bar_b_empty(g), bph ^ 1u);
+                const int g = (uint32_t)d0.row_n % ngr;
+                const uint32_t bph = ((uint32_t)d0.row_n / ngr) & 1u;
+                mbar_wait_relaxed(bar_b_empty(g), bph ^ 1u);
                 sts1(smem_base + OFF_BVEC + ((g * NTEAM + team) * F + m) * 4, (float)bacc);
                 mbar_arrive(bar_b_full(g, team));
                 bacc = 0.0;
@@ -487,10 +509,10 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                 const RowEnt e = nxt;
                 nxt = ent_at(k + 1);
                 if (e.n <= 0) continue;
-                const int g = row_n % NGROUP;
-                const uint32_t aph = (row_n / NGROUP) & 1u;
+                const int g = row_n % ngr;
+                const uint32_t aph = (row_n / ngr) & 1u;
                 if (prof) tt = clock64();
-                mbar_wait(bar_acc_empty(g), aph ^ 1u);
+                mbar_wait_relaxed(bar_acc_empty(g), aph ^ 1u);
                 if (prof) t_accempty += clock64() - tt;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
@@ -554,7 +576,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             nxt = ent_at(k + 1);
             if (e.n <= 0) continue;
             const uint32_t rn = row_n++;
-            if ((int)(rn % NGROUP) != g) continue;
+            if ((int)(rn % ngr) != g) continue;
             ++my_rows;
             tr = PROF && blockIdx.x == 0 && g == 0 && lane == 0 && my_rows == 60;
 #define STAMP(i) do { if (PROF && tr) trace[((q * 16 + (c0 >> 3)) * 8) + (i)] = clock64(); } while (0)
@@ -566,13 +588,13 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             {
                 float bA = 0.0f, bB = 0.0f;  // team 0, team 1
                 const bool both = e.n > SUB;
-                if (t0 == 0 || both) { mbar_wait(bar_b_full(g, 0), cnt_b0 & 1u); ++cnt_b0; bA = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 0) * F + t) * 4); }
-                if (t0 == 1 || both) { mbar_wait(bar_b_full(g, 1), cnt_b1 & 1u); ++cnt_b1; bB = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 1) * F + t) * 4); }
+                if (t0 == 0 || both) { mbar_wait_relaxed(bar_b_full(g, 0), cnt_b0 & 1u); ++cnt_b0; bA = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 0) * F + t) * 4); }
+                if (t0 == 1 || both) { mbar_wait_relaxed(bar_b_full(g, 1), cnt_b1 & 1u); ++cnt_b1; bB = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 1) * F + t) * 4); }
                 bt = bA + bB;
             }
             float dbg_val = bt;
             mbar_arrive(bar_b_empty(g));
-            mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
+            mbar_wait_relaxed(bar_acc_full(g), (rn / ngr) & 1u);
             tc_fence_after();
             if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
             // The columns of the current step live in registers, fully updated: they are read from TMEM one
@@ -600,38 +622,34 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                 }
                 STAMP(0);
                 if (prof) t3 = clock64();
+                const uint32_t Dk = Dblk + ((c0 >> 3) & 1) * DBLK_BYTES;  // double buffered: the next owner runs ahead
                 if (q == (c0 >> 5)) {
-                    // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
+                    // ---- owner warp: Cholesky of the 8x8 pivot block and its inverse N = L^-1 ----
                     if (rel >= 0 && rel < NB) {
-                        sts4(Dblk + rel * 32, a[0], a[1], a[2], a[3]);
-                        sts4(Dblk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
-                        sts1(Dblk + 256 + rel * 4, bt);
+                        sts4(Dk + rel * 32, a[0], a[1], a[2], a[3]);
+                        sts4(Dk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
+                        sts1(Dk + 256 + rel * 4, bt);
                     }
                     __syncwarp();
-                    float d[36], bb[NB];
+                    float d[36];
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
-                        const float4 d0 = lds4(Dblk + i * 32);
+                        const float4 d0 = lds4(Dk + i * 32);
                         d[TRI(i, 0)] = d0.x;
                         if (i >= 1) d[TRI(i, 1)] = d0.y;
                         if (i >= 2) d[TRI(i, 2)] = d0.z;
                         if (i >= 3) d[TRI(i, 3)] = d0.w;
                         if (i >= 4) {
-                            const float4 d1 = lds4(Dblk + i * 32 + 16);
+                            const float4 d1 = lds4(Dk + i * 32 + 16);
                             d[TRI(i, 4)] = d1.x;
                             if (i >= 5) d[TRI(i, 5)] = d1.y;
                             if (i >= 6) d[TRI(i, 6)] = d1.z;
                             if (i >= 7) d[TRI(i, 7)] = d1.w;
                         }
                     }
-                    {
-                        const float4 b0 = lds4(Dblk + 256), b1 = lds4(Dblk + 272);
-                        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
-                        bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-                    }
                     Factor8 fo;
-                    const bool ok = factor8(d, bb, fo);
-                    if (lane == 0) {  // published scaled: S N and zb / S, so P comes out as S P (the MMA operand) for free
+                    const bool ok = factor8(d, fo);
+                    if (lane == 0) {  // published as S N, so P comes out as S P (the MMA operand) for free
 #pragma unroll
                         for (int i = 0; i < NB; ++i) {
                             sts4(nd + i * 32, S * fo.n[TRI(i, 0)], i >= 1 ? S * fo.n[TRI(i, 1)] : 0.f,
@@ -640,11 +658,20 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                                 sts4(nd + i * 32 + 16, S * fo.n[TRI(i, 4)], i >= 5 ? S * fo.n[TRI(i, 5)] : 0.f,
                                      i >= 6 ? S * fo.n[TRI(i, 6)] : 0.f, i >= 7 ? S * fo.n[TRI(i, 7)] : 0.f);
                         }
-                        sts4(zd, inv_s * fo.zb[0], inv_s * fo.zb[1], inv_s * fo.zb[2], inv_s * fo.zb[3]);
-                        sts4(zd + 16, inv_s * fo.zb[4], inv_s * fo.zb[5], inv_s * fo.zb[6], inv_s * fo.zb[7]);
                         if (!ok) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
                     }
                     if (prof) { t4 = clock64(); ph_own += t4 - t3; }
+                }
+                // next step's columns: steps < k are in TMEM once the previous rank-8 update has landed (issued a whole
+                // pivot chain ago); the load is asynchronous and overlaps the barrier and the product below
+                uint32_t anr[NB];
+                if (more) {
+                    if (c0 > 0) {
+                        mbar_wait(bar_panel(g), panel_n & 1u);
+                        ++panel_n;
+                        tc_fence_after();
+                    }
+                    tmem_ld8_issue(t_row + c0 + NB, anr);
                 }
                 STAMP(1);
                 named_bar(bar_id, GROUP);
@@ -653,54 +680,46 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                 // are pivots (P = 0) ----
                 float P[NB];
                 {
+                    const float4 b0 = lds4(Dk + 256), b1 = lds4(Dk + 272);  // rhs of the pivot rows
+                    float w[NB];  // zb / S = (S N b_blk) / S^2
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
                         const float4 n0 = lds4(nd + jj * 32);
-                        float v = a[0] * n0.x;
-                        if (jj >= 1) v = fmaf(a[1], n0.y, v);
-                        if (jj >= 2) v = fmaf(a[2], n0.z, v);
-                        if (jj >= 3) v = fmaf(a[3], n0.w, v);
+                        float v = a[0] * n0.x, z = b0.x * n0.x;
+                        if (jj >= 1) { v = fmaf(a[1], n0.y, v); z = fmaf(b0.y, n0.y, z); }
+                        if (jj >= 2) { v = fmaf(a[2], n0.z, v); z = fmaf(b0.z, n0.z, z); }
+                        if (jj >= 3) { v = fmaf(a[3], n0.w, v); z = fmaf(b0.w, n0.w, z); }
                         if (jj >= 4) {
                             const float4 n1 = lds4(nd + jj * 32 + 16);
-                            v = fmaf(a[4], n1.x, v);
-                            if (jj >= 5) v = fmaf(a[5], n1.y, v);
-                            if (jj >= 6) v = fmaf(a[6], n1.z, v);
-                            if (jj >= 7) v = fmaf(a[7], n1.w, v);
+                            v = fmaf(a[4], n1.x, v); z = fmaf(b1.x, n1.x, z);
+                            if (jj >= 5) { v = fmaf(a[5], n1.y, v); z = fmaf(b1.y, n1.y, z); }
+                            if (jj >= 6) { v = fmaf(a[6], n1.z, v); z = fmaf(b1.z, n1.z, z); }
+                            if (jj >= 7) { v = fmaf(a[7], n1.w, v); z = fmaf(b1.w, n1.w, z); }
                         }
                         P[jj] = v;
+                        w[jj] = z * inv_s2;
                     }
                     if (q == (c0 >> 5)) {  // only the owner warp holds pivot rows
                         const bool pivot = rel >= 0 && rel < NB;
 #pragma unroll
                         for (int jj = 0; jj < NB; ++jj) P[jj] = pivot ? 0.0f : P[jj];
                     }
-                    const float4 z0 = lds4(zd), z1 = lds4(zd + 16);
-                    float u0 = P[0] * z0.x, u1 = P[1] * z0.y;  // two chains, fixed order
-                    u0 = fmaf(P[2], z0.z, u0); u1 = fmaf(P[3], z0.w, u1);
-                    u0 = fmaf(P[4], z1.x, u0); u1 = fmaf(P[5], z1.y, u1);
-                    u0 = fmaf(P[6], z1.z, u0); u1 = fmaf(P[7], z1.w, u1);
+                    float u0 = P[0] * w[0], u1 = P[1] * w[1];  // two chains, fixed order
+                    u0 = fmaf(P[2], w[2], u0); u1 = fmaf(P[3], w[3], u1);
+                    u0 = fmaf(P[4], w[4], u0); u1 = fmaf(P[5], w[5], u1);
+                    u0 = fmaf(P[6], w[6], u0); u1 = fmaf(P[7], w[7], u1);
                     bt -= u0 + u1;
                 }
                 STAMP(3);
                 if (more) {
-                    // next step's columns: steps < k are in TMEM once the previous update has landed; step k is applied below
-                    if (prof) t3 = clock64();
-                    if (c0 > 0) {
-                        mbar_wait(bar_panel(g), panel_n & 1u);
-                        ++panel_n;
-                        tc_fence_after();
-                    }
-                    if (prof) { t4 = clock64(); ph_wait += t4 - t3; }
-                    STAMP(4);
                     float an[NB];
-                    tmem_ld8(t_row + c0 + NB, an);
+                    tmem_ld_wait();
                     if (!update) {  // last read of the accumulator: the Gram of this group's next row may start
                         tc_fence_before();
                         mbar_arrive(bar_acc_empty(g));
                     }
 #pragma unroll
-                    for (int i = 0; i < NB; ++i) an[i] = fmaf(an[i], inv_s2, gg[i]);
-                    if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
+                    for (int i = 0; i < NB; ++i) an[i] = fmaf(__uint_as_float(anr[i]), inv_s2, gg[i]);
                     STAMP(5);
                     // The warp that owns the next pivot block is the critical path: it brings its columns up to
                     // date first (its own lanes hold the 8 rows of P it needs), only arrives at the hand-over
@@ -839,6 +858,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
         attr_set = true;
     }
     HalfStepParams p = in;
+    p.FP = getenv("WMF_TC_GROUPS") ? atoi(getenv("WMF_TC_GROUPS")) : 0;
     p.KC = getenv("WMF_TC_DEBUG") ? atoi(getenv("WMF_TC_DEBUG")) : 0;  // debug: 1 = output the rhs, 2+c = output column c of A
     p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
     const int sms = sm_count();
