@@ -70,10 +70,8 @@ constexpr int G_OFF_TILEL = G_OFF_TILEH + PANEL_TILE_BYTES;
 constexpr int G_OFF_NINV = G_OFF_TILEL + PANEL_TILE_BYTES;          // 16 blocks x (8 x 8) floats: N = L^-1 per pivot block
 constexpr int G_OFF_ZB = G_OFF_NINV + (F / NB) * NB * NB * 4;       // 16 x 8 floats: N b_blk
 constexpr int G_OFF_DBLK = G_OFF_ZB + (F / NB) * NB * 4;            // 8 x 8 pivot block + 8 rhs
-constexpr int DBLK_BYTES = (NB * NB + 2 * NB) * 4;                   // 320: 8 x 8 block, 8 rhs, pad
-constexpr int G_OFF_BFIN = G_OFF_DBLK + 2 * DBLK_BYTES;     // 128 floats: final rhs
-constexpr int G_OFF_PNX = G_OFF_BFIN + F * 4;                       // 8 x 8 floats: P rows of the next pivot block
-constexpr int GROUP_BYTES = ((G_OFF_PNX + NB * NB * 4 + 127) / 128) * 128;
+constexpr int G_OFF_BFIN = G_OFF_DBLK + (NB * NB + 2 * NB) * 4;     // 128 floats: final rhs
+constexpr int GROUP_BYTES = ((G_OFF_BFIN + F * 4 + 127) / 128) * 128;
 
 // shared memory carve-up (bytes from a 1024-aligned base)
 constexpr int OFF_STAGES = 0;                                        // NSTAGE/2 tile pairs
@@ -117,20 +115,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
         "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-}
-// waits that are not on a critical path back off between polls (polling was ~27 % of all issued instructions)
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(128);
-    }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -189,12 +173,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {  // results valid after tmem_ld_wait()
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -224,9 +202,6 @@ __device__ __forceinline__ void sts1(uint32_t a, float x) {
 }
 __device__ __forceinline__ void named_bar(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {  // non-blocking arrival
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -344,7 +319,6 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         return e;
     };
     const float S = gram_scale(hdr);
-    const uint32_t ngr = p.FP > 0 ? (uint32_t)p.FP : (uint32_t)NGROUP;  // experiment: active solver groups
 
     if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
         // =============================== GATHER ===============================
@@ -439,7 +413,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         while (d0.gi >= 0) {
             if (prof) t2 = clock64();
             // buffer (j+2)%3 was read by every thread of the team during iteration j-1: barrier before refilling it
-            named_bar(1 + 2 * NGROUP + team, TEAM);
+            named_bar(1 + NGROUP + team, TEAM);
             const Desc d3 = describe();
             issue(r2, (j + 2) % NSTG);   // sub-chunk j+2
             r2 = load_raw();             // sub-chunk j+3, first touched next iteration
@@ -448,7 +422,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             if (prof) { tt = clock64(); t_issue += tt - t2; }
             mbar_wait(bar_stg(team, sb), (j / NSTG) & 1u);
             if (prof) { t2 = clock64(); t_stg += t2 - tt; }
-            mbar_wait_relaxed(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
+            mbar_wait(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
             if (prof) { tt = clock64(); t_empty += tt - t2; }
             const uint32_t stg = smem_base + OFF_STG + (team * NSTG + sb) * STG_BYTES + m * 4;
             const uint32_t mt = smem_base + OFF_META + (team * NSTG + sb) * META_BYTES;
@@ -484,9 +458,9 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             mbar_arrive(bar_full(s));
             if (prof) { t2 = clock64(); t_xform += t2 - tt; }
             if (d0.last) {  // hand the team's rhs partial to the solver group that owns this row
-                const int g = (uint32_t)d0.row_n % ngr;
-                const uint32_t bph = ((uint32_t)d0.row_n / ngr) & 1u;
-                mbar_wait_relaxed(bar_b_empty(g), bph ^ 1u);
+                const int g = d0.row_n % NGROUP;
+                const uint32_t bph = ((uint32_t)d0.row_n / NGROUP) & 1u;
+                mbar_wait(bar_b_empty(g), bph ^ 1u);
                 sts1(smem_base + OFF_BVEC + ((g * NTEAM + team) * F + m) * 4, (float)bacc);
                 mbar_arrive(bar_b_full(g, team));
                 bacc = 0.0;
@@ -509,10 +483,10 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                 const RowEnt e = nxt;
                 nxt = ent_at(k + 1);
                 if (e.n <= 0) continue;
-                const int g = row_n % ngr;
-                const uint32_t aph = (row_n / ngr) & 1u;
+                const int g = row_n % NGROUP;
+                const uint32_t aph = (row_n / NGROUP) & 1u;
                 if (prof) tt = clock64();
-                mbar_wait_relaxed(bar_acc_empty(g), aph ^ 1u);
+                mbar_wait(bar_acc_empty(g), aph ^ 1u);
                 if (prof) t_accempty += clock64() - tt;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
@@ -558,7 +532,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         const int bar_id = 1 + g;
         const uint32_t gs = smem_base + OFF_GROUPS + g * GROUP_BYTES;
         const uint32_t tileH = gs + G_OFF_TILEH, tileL = gs + G_OFF_TILEL;
-        const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN, Pnx = gs + G_OFF_PNX;
+        const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * F);
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
@@ -566,8 +540,6 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         const float inv_s = 1.0f / S, inv_s2 = inv_s * inv_s;  // exact: S is a power of two
         uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
-        long long* trace = PROF ? reinterpret_cast<long long*>(const_cast<RowEnt*>(rowtab) + p.sched_len) : nullptr;
-        bool tr = false;  // lane 0 of every warp of group 0 / CTA 0 stamps one row
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
         long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0, my_rows = 0;
         RowEnt nxt = ent_at(0);
@@ -576,10 +548,8 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             nxt = ent_at(k + 1);
             if (e.n <= 0) continue;
             const uint32_t rn = row_n++;
-            if ((int)(rn % ngr) != g) continue;
+            if ((int)(rn % NGROUP) != g) continue;
             ++my_rows;
-            tr = PROF && blockIdx.x == 0 && g == 0 && lane == 0 && my_rows == 60;
-#define STAMP(i) do { if (PROF && tr) trace[((q * 16 + (c0 >> 3)) * 8) + (i)] = clock64(); } while (0)
             float* xout = p.X + (int64_t)e.row * p.ldx;
             if (prof) tt = clock64();
             // rhs partials: the team that owns sub-chunk 0 always delivers, the other one if the row has two or more
@@ -588,68 +558,71 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             {
                 float bA = 0.0f, bB = 0.0f;  // team 0, team 1
                 const bool both = e.n > SUB;
-                if (t0 == 0 || both) { mbar_wait_relaxed(bar_b_full(g, 0), cnt_b0 & 1u); ++cnt_b0; bA = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 0) * F + t) * 4); }
-                if (t0 == 1 || both) { mbar_wait_relaxed(bar_b_full(g, 1), cnt_b1 & 1u); ++cnt_b1; bB = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 1) * F + t) * 4); }
+                if (t0 == 0 || both) { mbar_wait(bar_b_full(g, 0), cnt_b0 & 1u); ++cnt_b0; bA = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 0) * F + t) * 4); }
+                if (t0 == 1 || both) { mbar_wait(bar_b_full(g, 1), cnt_b1 & 1u); ++cnt_b1; bB = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 1) * F + t) * 4); }
                 bt = bA + bB;
             }
             float dbg_val = bt;
             mbar_arrive(bar_b_empty(g));
-            mbar_wait_relaxed(bar_acc_full(g), (rn / ngr) & 1u);
+            mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
             tc_fence_after();
             if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
-            // The columns of the current step live in registers, fully updated: they are read from TMEM one
-            // step ahead (when the rank-8 update of step k-1 has landed) and step k is applied to them in
-            // registers, so the tensor-core round trip of step k overlaps the pivot chain of step k+1.
-            float a[NB];
-            {
-                float gg[NB];
-#pragma unroll
-                for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + i * F);
-                tmem_ld8(t_row, a);
-#pragma unroll
-                for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, gg[i]);
-            }
 #pragma unroll 1
             for (int c0 = 0; c0 < F; c0 += NB) {
-                const int rel = t - c0;
-                const bool more = c0 + NB < F;          // another step follows
-                const bool update = c0 + 2 * NB < F;    // columns beyond the next step exist: rank-8 update on the tensor core
-                const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
-                float gg[NB];  // G entries of the next step's columns (in flight during the pivot chain)
-                if (more) {
+                float gg[NB];
 #pragma unroll
-                    for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + (c0 + NB + i) * F);
-                }
-                STAMP(0);
+                for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + (c0 + i) * F);
                 if (prof) t3 = clock64();
-                const uint32_t Dk = Dblk + ((c0 >> 3) & 1) * DBLK_BYTES;  // double buffered: the next owner runs ahead
+                if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
+                    mbar_wait(bar_panel(g), panel_n & 1u);
+                    ++panel_n;
+                    tc_fence_after();
+                }
+                if (prof) { t4 = clock64(); ph_wait += t4 - t3; }
+                float a[NB];
+                tmem_ld8(t_row + c0, a);
+                if (c0 + NB == F) {  // last read of the accumulator: the Gram of this group's next row may start
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty(g));
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, gg[i]);
+                if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
+                if (p.KC >= 2 && c0 == ((p.KC - 2) >> 3) * 8) dbg_val = a[(p.KC - 2) & 7];  // debug: column KC-2 of A
+                const int rel = t - c0;
+                const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
                 if (q == (c0 >> 5)) {
-                    // ---- owner warp: Cholesky of the 8x8 pivot block and its inverse N = L^-1 ----
+                    // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
                     if (rel >= 0 && rel < NB) {
-                        sts4(Dk + rel * 32, a[0], a[1], a[2], a[3]);
-                        sts4(Dk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
-                        sts1(Dk + 256 + rel * 4, bt);
+                        sts4(Dblk + rel * 32, a[0], a[1], a[2], a[3]);
+                        sts4(Dblk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
+                        sts1(Dblk + 256 + rel * 4, bt);
                     }
                     __syncwarp();
-                    float d[36];
+                    float d[36], bb[NB];
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
-                        const float4 d0 = lds4(Dk + i * 32);
+                        const float4 d0 = lds4(Dblk + i * 32);
                         d[TRI(i, 0)] = d0.x;
                         if (i >= 1) d[TRI(i, 1)] = d0.y;
                         if (i >= 2) d[TRI(i, 2)] = d0.z;
                         if (i >= 3) d[TRI(i, 3)] = d0.w;
                         if (i >= 4) {
-                            const float4 d1 = lds4(Dk + i * 32 + 16);
+                            const float4 d1 = lds4(Dblk + i * 32 + 16);
                             d[TRI(i, 4)] = d1.x;
                             if (i >= 5) d[TRI(i, 5)] = d1.y;
                             if (i >= 6) d[TRI(i, 6)] = d1.z;
                             if (i >= 7) d[TRI(i, 7)] = d1.w;
                         }
                     }
+                    {
+                        const float4 b0 = lds4(Dblk + 256), b1 = lds4(Dblk + 272);
+                        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+                        bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+                    }
                     Factor8 fo;
-                    const bool ok = factor8(d, fo);
-                    if (lane == 0) {  // published as S N, so P comes out as S P (the MMA operand) for free
+                    const bool ok = factor8(d, bb, fo);
+                    if (lane == 0) {  // published scaled: S N and zb / S, so P comes out as S P (the MMA operand) for free
 #pragma unroll
                         for (int i = 0; i < NB; ++i) {
                             sts4(nd + i * 32, S * fo.n[TRI(i, 0)], i >= 1 ? S * fo.n[TRI(i, 1)] : 0.f,
@@ -658,133 +631,74 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                                 sts4(nd + i * 32 + 16, S * fo.n[TRI(i, 4)], i >= 5 ? S * fo.n[TRI(i, 5)] : 0.f,
                                      i >= 6 ? S * fo.n[TRI(i, 6)] : 0.f, i >= 7 ? S * fo.n[TRI(i, 7)] : 0.f);
                         }
+                        sts4(zd, inv_s * fo.zb[0], inv_s * fo.zb[1], inv_s * fo.zb[2], inv_s * fo.zb[3]);
+                        sts4(zd + 16, inv_s * fo.zb[4], inv_s * fo.zb[5], inv_s * fo.zb[6], inv_s * fo.zb[7]);
                         if (!ok) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
                     }
                     if (prof) { t4 = clock64(); ph_own += t4 - t3; }
                 }
-                // next step's columns: steps < k are in TMEM once the previous rank-8 update has landed (issued a whole
-                // pivot chain ago); the load is asynchronous and overlaps the barrier and the product below
-                uint32_t anr[NB];
-                if (more) {
-                    if (c0 > 0) {
-                        mbar_wait(bar_panel(g), panel_n & 1u);
-                        ++panel_n;
-                        tc_fence_after();
-                    }
-                    tmem_ld8_issue(t_row + c0 + NB, anr);
-                }
-                STAMP(1);
                 named_bar(bar_id, GROUP);
-                STAMP(2);
                 // ---- every row outside the block: P = a (S N)^T = S a N^T, rhs -= P (zb / S); the block's own rows
                 // are pivots (P = 0) ----
                 float P[NB];
                 {
-                    const float4 b0 = lds4(Dk + 256), b1 = lds4(Dk + 272);  // rhs of the pivot rows
-                    float w[NB];  // zb / S = (S N b_blk) / S^2
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
                         const float4 n0 = lds4(nd + jj * 32);
-                        float v = a[0] * n0.x, z = b0.x * n0.x;
-                        if (jj >= 1) { v = fmaf(a[1], n0.y, v); z = fmaf(b0.y, n0.y, z); }
-                        if (jj >= 2) { v = fmaf(a[2], n0.z, v); z = fmaf(b0.z, n0.z, z); }
-                        if (jj >= 3) { v = fmaf(a[3], n0.w, v); z = fmaf(b0.w, n0.w, z); }
+                        float v = a[0] * n0.x;
+                        if (jj >= 1) v = fmaf(a[1], n0.y, v);
+                        if (jj >= 2) v = fmaf(a[2], n0.z, v);
+                        if (jj >= 3) v = fmaf(a[3], n0.w, v);
                         if (jj >= 4) {
                             const float4 n1 = lds4(nd + jj * 32 + 16);
-                            v = fmaf(a[4], n1.x, v); z = fmaf(b1.x, n1.x, z);
-                            if (jj >= 5) { v = fmaf(a[5], n1.y, v); z = fmaf(b1.y, n1.y, z); }
-                            if (jj >= 6) { v = fmaf(a[6], n1.z, v); z = fmaf(b1.z, n1.z, z); }
-                            if (jj >= 7) { v = fmaf(a[7], n1.w, v); z = fmaf(b1.w, n1.w, z); }
+                            v = fmaf(a[4], n1.x, v);
+                            if (jj >= 5) v = fmaf(a[5], n1.y, v);
+                            if (jj >= 6) v = fmaf(a[6], n1.z, v);
+                            if (jj >= 7) v = fmaf(a[7], n1.w, v);
                         }
                         P[jj] = v;
-                        w[jj] = z * inv_s2;
                     }
                     if (q == (c0 >> 5)) {  // only the owner warp holds pivot rows
                         const bool pivot = rel >= 0 && rel < NB;
 #pragma unroll
                         for (int jj = 0; jj < NB; ++jj) P[jj] = pivot ? 0.0f : P[jj];
                     }
-                    float u0 = P[0] * w[0], u1 = P[1] * w[1];  // two chains, fixed order
-                    u0 = fmaf(P[2], w[2], u0); u1 = fmaf(P[3], w[3], u1);
-                    u0 = fmaf(P[4], w[4], u0); u1 = fmaf(P[5], w[5], u1);
-                    u0 = fmaf(P[6], w[6], u0); u1 = fmaf(P[7], w[7], u1);
+                    const float4 z0 = lds4(zd), z1 = lds4(zd + 16);
+                    float u0 = P[0] * z0.x, u1 = P[1] * z0.y;  // two chains, fixed order
+                    u0 = fmaf(P[2], z0.z, u0); u1 = fmaf(P[3], z0.w, u1);
+                    u0 = fmaf(P[4], z1.x, u0); u1 = fmaf(P[5], z1.y, u1);
+                    u0 = fmaf(P[6], z1.z, u0); u1 = fmaf(P[7], z1.w, u1);
                     bt -= u0 + u1;
                 }
-                STAMP(3);
-                if (more) {
-                    float an[NB];
-                    tmem_ld_wait();
-                    if (!update) {  // last read of the accumulator: the Gram of this group's next row may start
-                        tc_fence_before();
-                        mbar_arrive(bar_acc_empty(g));
+                if (c0 + NB < F) {
+                    float lh[NB], ll[NB];
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
+                        lh[jj] = tf32_round(P[jj]);
+                        ll[jj] = P[jj] - lh[jj];  // exact; the tensor core reads its top 19 bits (error 2^-23 of P)
                     }
-#pragma unroll
-                    for (int i = 0; i < NB; ++i) an[i] = fmaf(__uint_as_float(anr[i]), inv_s2, gg[i]);
-                    STAMP(5);
-                    // The warp that owns the next pivot block is the critical path: it brings its columns up to
-                    // date first (its own lanes hold the 8 rows of P it needs), only arrives at the hand-over
-                    // barrier and goes straight on to the next Cholesky; the other warps publish their tile,
-                    // one of them issues the rank-8 update, and they update their registers afterwards.
-                    const int nq = (c0 + NB) >> 5;
-                    auto publish_tile = [&]() {
-                        float lh[NB], ll[NB];
-#pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
-                            lh[jj] = tf32_round(P[jj]);
-                            ll[jj] = P[jj] - lh[jj];  // exact; the tensor core reads its top 19 bits (error 2^-23 of P)
-                        }
-                        const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
-                        sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
-                        sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
-                        sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
-                        sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
-                        fence_async_smem();
-                    };
-                    auto update_regs = [&]() {  // a_next -= P P_next^T
-#pragma unroll
-                        for (int jj = 0; jj < NB; ++jj) {
-                            const float4 n0 = lds4(Pnx + jj * 32), n1 = lds4(Pnx + jj * 32 + 16);
-                            float u0 = P[0] * n0.x, u1 = P[1] * n0.y;
-                            u0 = fmaf(P[2], n0.z, u0); u1 = fmaf(P[3], n0.w, u1);
-                            u0 = fmaf(P[4], n1.x, u0); u1 = fmaf(P[5], n1.y, u1);
-                            u0 = fmaf(P[6], n1.z, u0); u1 = fmaf(P[7], n1.w, u1);
-                            a[jj] = an[jj] - (u0 + u1);
-                        }
-                    };
-                    if (q == nq) {
-                        // rows of the next pivot block publish their P (times 1/S^2: the product with S P is then unscaled)
-                        if (rel >= NB && rel < 2 * NB) {
-                            sts4(Pnx + (rel - NB) * 32, P[0] * inv_s2, P[1] * inv_s2, P[2] * inv_s2, P[3] * inv_s2);
-                            sts4(Pnx + (rel - NB) * 32 + 16, P[4] * inv_s2, P[5] * inv_s2, P[6] * inv_s2, P[7] * inv_s2);
-                        }
-                        __syncwarp();
-                        update_regs();
-                        if (update) publish_tile();
-                        tc_fence_before();
-                        named_bar_arrive(bar_id + NGROUP, GROUP);
-                        STAMP(6);
-                    } else {
-                        if (update) publish_tile();
-                        tc_fence_before();
-                        if (prof) t3 = clock64();
-                        named_bar(bar_id + NGROUP, GROUP);
-                        STAMP(6);
-                        if (update && q == ((nq + 2) & 3) && lane == 0) {
-                            // S[:, j] -= P P[j]^T for the columns beyond the next step (all 128 rows: Gauss-Jordan)
-                            tc_fence_after();
-                            if (prof) { t4 = clock64(); ph_p += t4 - t3; }
-                            const uint32_t start = (uint32_t)((c0 + 2 * NB) >> 4) << 4;
-                            const uint32_t idesc = IDESC_TF32_NEG_M128 | (((F - start) >> 3) << 17);
-                            const uint64_t bH = descH + (uint64_t)(start * 2), bL = descL + (uint64_t)(start * 2);
-                            umma_tf32(d_tmem + start, descH, bH, idesc, 1u);
-                            umma_tf32(d_tmem + start, descH, bL, idesc, 1u);
-                            umma_tf32(d_tmem + start, descL, bH, idesc, 1u);
-                            tc_commit(bar_panel(g));
-                            if (prof) ph_issue += clock64() - t4;
-                        }
-                        update_regs();
+                    const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+                    sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
+                    sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
+                    sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
+                    sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
+                    fence_async_smem();
+                    tc_fence_before();
+                    if (prof) t3 = clock64();
+                    named_bar(bar_id, GROUP);
+                    if (t == 0) {
+                        // S[:, j] -= P P[j]^T for the live columns j >= c0 + 8 (all 128 rows: Gauss-Jordan)
+                        tc_fence_after();
+                        if (prof) { t4 = clock64(); ph_p += t4 - t3; }
+                        const uint32_t start = (uint32_t)((c0 + NB) >> 4) << 4;
+                        const uint32_t idesc = IDESC_TF32_NEG_M128 | (((F - start) >> 3) << 17);
+                        const uint64_t bH = descH + (uint64_t)(start * 2), bL = descL + (uint64_t)(start * 2);
+                        umma_tf32(d_tmem + start, descH, bH, idesc, 1u);
+                        umma_tf32(d_tmem + start, descH, bL, idesc, 1u);
+                        umma_tf32(d_tmem + start, descL, bH, idesc, 1u);
+                        tc_commit(bar_panel(g));
+                        if (prof) ph_issue += clock64() - t4;
                     }
-                    STAMP(7);
                 }
             }
             if (prof) { t_fact += clock64() - tt; tt = clock64(); }
@@ -858,7 +772,6 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
         attr_set = true;
     }
     HalfStepParams p = in;
-    p.FP = getenv("WMF_TC_GROUPS") ? atoi(getenv("WMF_TC_GROUPS")) : 0;
     p.KC = getenv("WMF_TC_DEBUG") ? atoi(getenv("WMF_TC_DEBUG")) : 0;  // debug: 1 = output the rhs, 2+c = output column c of A
     p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
     const int sms = sm_count();

@@ -38,6 +38,44 @@ def default_device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_pinned = {}
+
+
+def _h2d(arr, dtype, device):
+    """Host array -> device tensor. Large arrays go through a cached pinned staging buffer (filled by a
+    multi-threaded host copy) so the transfer itself runs at PCIe rate instead of the pageable path's."""
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    t = torch.from_numpy(a)
+    n = t.numel()
+    if a.nbytes < (4 << 20) or device.type != "cuda":
+        return t.to(device, non_blocking=True)
+    key = (t.dtype, device.index)
+    ent = _pinned.get(key)
+    if ent is None or ent[0].numel() < n:
+        ent = [torch.empty(max(n, 1 << 20), dtype=t.dtype, pin_memory=True), None]
+        _pinned[key] = ent
+    buf, busy = ent
+    if busy is not None:
+        busy.synchronize()  # the previous transfer out of this staging buffer has finished
+    buf[:n].copy_(t)
+    out = buf[:n].to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    ent[1] = ev
+    return out
+
+
+def d2h(t):
+    """Device tensor -> NumPy array backed by pinned host memory from torch's caching host allocator
+    (a fresh pageable array costs tens of ms in first-touch page faults at 85 MB)."""
+    if not t.is_cuda:
+        return t.numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
 def _f32(t):
     assert t.dtype == torch.float32 and t.is_cuda and t.stride(-1) == 1, "expected a row-major float32 CUDA tensor"
     return t
@@ -60,9 +98,9 @@ class DeviceCSR:
         mat = mat.tocsr()
         if mat.shape[1] >= 2 ** 31:
             raise ValueError("column count must fit int32")
-        indptr = torch.from_numpy(np.ascontiguousarray(mat.indptr, dtype=np.int64)).to(device, non_blocking=True)
-        indices = torch.from_numpy(np.ascontiguousarray(mat.indices, dtype=np.int32)).to(device, non_blocking=True)
-        data = torch.from_numpy(np.ascontiguousarray(mat.data, dtype=np.float32)).to(device, non_blocking=True)
+        indptr = _h2d(mat.indptr, np.int64, device)
+        indices = _h2d(mat.indices, np.int32, device)
+        data = _h2d(mat.data, np.float32, device)
         return cls(indptr, indices, data, mat.shape)
 
     @property
@@ -72,11 +110,10 @@ class DeviceCSR:
     @property
     def row_order(self):
         """Processing schedule for the half-step kernels (see include/wmf_b200.h): rows sorted
-        longest first and dealt to the persistent CTAs in rounds, each round giving its
-        heaviest row to the currently lightest CTA. int32, -1 = padding slot."""
+        longest first (one stable device sort) and dealt to the persistent CTAs in rounds, each
+        round giving its heaviest row to the currently lightest CTA. int32, -1 = padding slot."""
         if self._row_order is None:
-            counts = (self.indptr[1:] - self.indptr[:-1]).cpu().numpy()
-            self._row_order = torch.from_numpy(balanced_schedule(counts, _lib.require_device())).to(self.device)
+            self._row_order = device_schedule(self.indptr, _lib.require_device())
         return self._row_order
 
     def with_data(self, data):
@@ -113,50 +150,84 @@ class DeviceCSR:
                                        shape=self.shape)
 
 
+def device_schedule(indptr, n_cta, chunk=32, row_overhead=4):
+    """``balanced_schedule`` with the O(rows log rows) part on the device: the rows are sorted by
+    length there; when no row is heavy (the common case) the padded sorted order IS the schedule
+    and nothing but two scalars crosses to the host. With a heavy head only the sorted costs go to
+    the host for the greedy placement."""
+    counts = indptr[1:] - indptr[:-1]
+    rows = counts.numel()
+    if rows == 0:
+        return torch.full((n_cta,), -1, dtype=torch.int32, device=indptr.device)
+    sorted_counts, order = torch.sort(counts, descending=True, stable=True)
+    cost = torch.where(sorted_counts > 0, (sorted_counts + (chunk - 1)) // chunk + row_overhead,
+                       torch.zeros_like(sorted_counts))
+    head = torch.stack((cost[0], cost.sum())).cpu()
+    mean_load = float(head[1]) / n_cta
+    if float(head[0]) < 0.05 * mean_load:  # no heavy head: round-robin over the sorted rows is balanced
+        sched = torch.full((((rows + n_cta - 1) // n_cta) * n_cta,), -1, dtype=torch.int32, device=indptr.device)
+        sched[:rows] = order.to(torch.int32)
+        return sched
+    sched = _schedule_from_sorted(order.cpu().numpy(), cost.cpu().numpy(), n_cta)
+    return torch.from_numpy(sched).to(indptr.device)
+
+
 def balanced_schedule(counts, n_cta, chunk=32, row_overhead=4):
-    """Longest-processing-time schedule for the persistent CTAs. Cost of a row = its 32-entry
-    chunks plus a fixed solve overhead. Returns int32[n_slots * n_cta]; slot k*n_cta + c is
-    the k-th row of CTA c, -1 where that CTA has no k-th row (a CTA that owns a very long row
-    takes fewer rows)."""
-    import heapq
+    """Longest-processing-time schedule for the persistent CTAs (host version of
+    ``device_schedule``). Cost of a row = its 32-entry chunks plus a fixed solve overhead. Returns
+    int32[n_slots * n_cta]; slot k*n_cta + c is the k-th row of CTA c, -1 where that CTA has no
+    k-th row (a CTA that owns a very long row takes fewer rows)."""
     counts = np.asarray(counts, dtype=np.int64)
     rows = len(counts)
-    order = np.argsort(-counts, kind="stable")
-    cost = np.where(counts > 0, (counts + chunk - 1) // chunk + row_overhead, 0).astype(np.int64)[order]
     if rows == 0:
         return np.full(n_cta, -1, dtype=np.int32)
+    order = np.argsort(-counts, kind="stable")
+    cost = np.where(counts > 0, (counts + chunk - 1) // chunk + row_overhead, 0).astype(np.int64)[order]
     mean_load = cost.sum() / n_cta
     if cost[0] < 0.05 * mean_load:  # no heavy head: round-robin over the sorted rows is balanced
         sched = np.full(((rows + n_cta - 1) // n_cta) * n_cta, -1, dtype=np.int32)
         sched[:rows] = order
         return sched
-    # heavy head: greedy LPT for the rows that matter, round-robin over the lightest CTAs for the tail
+    return _schedule_from_sorted(order, cost, n_cta)
+
+
+def _schedule_from_sorted(order, cost, n_cta):
+    """Heavy head: greedy LPT for the rows that matter, then rounds over the currently lightest
+    CTAs. ``assign[k]`` = CTA of the k-th heaviest row; the schedule is built from it in one pass."""
+    import heapq
+    rows = len(order)
+    order = np.asarray(order, dtype=np.int64)
+    cost = np.asarray(cost, dtype=np.int64)
+    mean_load = cost.sum() / n_cta
+    assign = np.empty(rows, dtype=np.int64)
     n_head = int(np.searchsorted(-cost, -max(1, int(0.01 * mean_load)), side="right"))
-    lists = [[] for _ in range(n_cta)]
     heap = [(0, c) for c in range(n_cta)]
+    head_cost = cost[:n_head].tolist()
     for k in range(n_head):
         load, c = heapq.heappop(heap)
-        lists[c].append(order[k])
-        heapq.heappush(heap, (load + int(cost[k]), c))
+        assign[k] = c
+        heapq.heappush(heap, (load + head_cost[k], c))
     load = np.zeros(n_cta)
     for l, c in heap:
         load[c] = l
     k = n_head
-    while k < rows:  # tail rows are tiny: hand them out in rounds to the currently lightest CTAs
+    remaining = float(cost[k:].sum())
+    total = float(load.sum()) + remaining
+    while k < rows:  # tail rows are small: hand them out in rounds to the currently lightest CTAs
         take = min(n_cta, rows - k)
-        target = (load.sum() + cost[k:].sum()) / n_cta
         ctas = np.argsort(load, kind="stable")
-        ctas = ctas[load[ctas] < target][:take]
-        if len(ctas) == 0:
-            ctas = np.argsort(load, kind="stable")[:take]
-        for j, c in enumerate(ctas):
-            lists[c].append(order[k + j])
-        load[ctas] += cost[k:k + len(ctas)]
-        k += len(ctas)
-    n_slots = max(len(l) for l in lists)
-    sched = np.full((n_slots, n_cta), -1, dtype=np.int32)
-    for c, l in enumerate(lists):
-        sched[:len(l), c] = l
+        below = ctas[load[ctas] < total / n_cta][:take]
+        ctas = below if len(below) else ctas[:take]
+        n = len(ctas)
+        assign[k:k + n] = ctas
+        load[ctas] += cost[k:k + n]
+        k += n
+    by_cta = np.argsort(assign, kind="stable")           # rows grouped by CTA, heaviest first inside a CTA
+    per_cta = np.bincount(assign, minlength=n_cta)
+    starts = np.concatenate(([0], np.cumsum(per_cta)[:-1]))
+    slot = np.arange(rows) - np.repeat(starts, per_cta)
+    sched = np.full((int(per_cta.max()), n_cta), -1, dtype=np.int32)
+    sched[slot, assign[by_cta]] = order[by_cta]
     return sched.reshape(-1)
 
 

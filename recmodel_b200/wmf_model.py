@@ -68,7 +68,7 @@ class WMF(RecModel):
     @property
     def items(self):
         if self._items_h is None and self._items_d is not None:
-            self._items_h = self._items_d.cpu().numpy()
+            self._items_h = engine.d2h(self._items_d)
         return self._items_h
 
     @items.setter
@@ -79,7 +79,7 @@ class WMF(RecModel):
     @property
     def users(self):
         if self._users_h is None and self._users_d is not None:
-            self._users_h = self._users_d.cpu().numpy()
+            self._users_h = engine.d2h(self._users_d)
         return self._users_h
 
     @users.setter

@@ -22,6 +22,6 @@ def sched(c):
 T("schedule users", lambda: sched(Cd)); T("schedule items", lambda: sched(CT))
 Ed = T("DeviceCSR.from_scipy(eval)", lambda: DeviceCSR.from_scipy(te, dev))
 T("eval sddmm", lambda: engine.sddmm_loss(Ed, m.users_device, m.items_device))
-T("factors D2H", lambda: (m._users_d.cpu().numpy(), m._items_d.cpu().numpy()))
+T("factors D2H", lambda: (engine.d2h(m._users_d), engine.d2h(m._items_d)))
 T("tr.tocsr()", lambda: tr.tocsr())
 T("np.ascontiguousarray int64 indptr", lambda: np.ascontiguousarray(tr.indptr, dtype=np.int64))

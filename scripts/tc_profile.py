@@ -28,15 +28,6 @@ def run(csr, Yd, name):
     print("  gather phases: issue", f(prof[11]), "wait_stg", f(prof[5]), "xform", f(prof[12]), "arrive", f(prof[13]))
     print("  solver phases (thread 0 of group 0): wait_mma", f(prof[24]), "tmem_ld", f(prof[25]), "own_factor(4 of 16 panels)", f(prof[26]),
           "barA", f(prof[27]), "P", f(prof[28]), "split+sts+fence", f(prof[29]), "barB", f(prof[30]), "mma_issue", f(prof[31]))
-    if os.environ.get("WMF_TC_TRACE"):
-        import numpy as np
-        n_sched = csr.row_order.numel()
-        tr = ws[1024 + 16 * n_sched: 1024 + 16 * n_sched + 4 * 16 * 8 * 8].view(torch.int64).cpu().numpy().reshape(4, 16, 8)
-        base = tr[tr > 0].min()
-        names = ["start", "pre-barA", "post-barA", "P done", "mma waited", "ld done", "barB", "upd done"]
-        print("  trace (cycles from first stamp; rows: panel; per warp q0..q3):")
-        for pnl in range(16):
-            print("   panel %2d owner q%d: " % (pnl, pnl // 4) + " | ".join(" ".join("%6d" % (tr[q, pnl, i] - base if tr[q, pnl, i] else -1) for i in range(8)) for q in range(4)))
     return X
 U = run(Cd, Y, "user half-step")
 run(CT, U, "item half-step")
