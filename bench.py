@@ -42,6 +42,18 @@ def env_int(name, default):
         return default
 
 
+def load_traffic():
+    """DRAM bytes (read + write) of the two half-step launches of one epoch from the committed
+    `ncu --set full` capture (profiles/r01_ncu_traffic.json); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        return float(t["user_half_step_dram_bytes"]) + float(t["item_half_step_dram_bytes"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -68,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -294,6 +306,8 @@ def run_ours(args):
 
     e2e_step()  # warm-up (allocator, pinned staging)
     sync_all()
+    e2e_step()  # second warm-up: pinned staging / host allocator caches reach steady state
+    sync_all()
     times, d2h = [], 0
     for _ in range(e2e_steps):
         sync_all()
@@ -323,12 +337,16 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (2 x 160 MB CSR + 85 MB factors streamed per epoch)",
                        "algo": args.algo, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "als_half_step (2 launches/epoch)",
+                         "traffic": load_traffic() if world == 1 else None,
+                         "traffic_note": "DRAM read+write bytes of the same two launches (ncu --set full, profiles/); "
+                                         "algorithmic bytes = %d" % (bytes_user + bytes_item),
+                         "peak_kind": peak_kind, "kernel": "als_half_step (2 launches/epoch)",
                          "ms_user_half_step": t_user, "ms_item_half_step": t_item,
                          "fp32_equiv_tflops": flops / ((t_user + t_item) * 1e-3) / 1e12},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "nnz-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) * 1e3,
+                    "ms_steps_rank0": [round(t * 1e3, 2) for t in times],
                     "what": "WMF.train(host CSR, iterations=1) incl. upload, preprocess, transpose, epoch, eval_prec, "
                             "factor read-back; 80/20 split so nnz = train nnz"},
             "gpu_launches": 6 * args.steps,
