@@ -86,13 +86,14 @@ constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                // + slack f
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_GROUPS % 128 == 0 && GROUP_BYTES % 128 == 0 && OFF_BARS % 8 == 0 && OFF_STG % 1024 == 0, "alignment");
 
-// workspace layout (bytes): [0] SIMT row counter, [4] redo flags, [8] max diag(G) bits, [12] max|d| bits,
+// workspace layout (bytes): [0] SIMT row counter, [4] redo flags, [8] max diag(G),
 // [256, 768) profile slots, [1024, ...) row table
 constexpr size_t WS_PROF = 256, WS_ROWTAB = 1024;
 struct __align__(16) RowEnt {
-    int32_t row;  // CSR row id, -1 = padding slot
-    int32_t n;    // stored entries (0: nothing to do, X row already zeroed)
-    int64_t lo;   // indptr[row]
+    int32_t row;   // CSR row id, -1 = padding slot
+    int32_t n;     // stored entries (0: nothing to do, X row already zeroed)
+    int64_t lo;    // indptr[row] (48 bits when packed in the table)
+    int32_t sexp;  // S = 2^sexp for this row (the table packs it into the top 16 bits of lo)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,55 +206,56 @@ __device__ __forceinline__ void named_bar(int id, int count) {
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
-// S = 2^e with S * sqrt(max diag G) * sqrt(max|d|) just below the FP16 maximum. diag(G) = sum y^2 +
+// S = 2^e with S * sqrt(max diag G) * sqrt(max|d| of the row) just below the FP16 maximum. diag(G) = sum y^2 +
 // lambda bounds every y^2, so zh cannot overflow; the bound is loose by up to sqrt(#rows of Y), which
-// only moves the point below which zl becomes subnormal (entries that small do not matter).
-__device__ __forceinline__ float gram_scale(const float* hdr) {
-    const float m = sqrtf(hdr[2]) * sqrtf(hdr[3]);
-    if (!(m > 0.0f) || !(m < 3.0e38f)) return 1.0f;
+// only moves the point below which zl becomes subnormal (entries that small do not matter). The scale is
+// per ROW (not per call) so that a row's arithmetic does not depend on which rows share its launch:
+// row-sharded runs stay bitwise equal to single-GPU runs.
+__device__ __forceinline__ int gram_scale_exp(float max_diag_g, float max_d) {
+    const float m = sqrtf(max_diag_g) * sqrtf(max_d);
+    if (!(m > 0.0f) || !(m < 3.0e38f)) return 0;
     int e = (int)floorf(log2f(60000.0f / m));
-    e = e > 40 ? 40 : (e < -40 ? -40 : e);  // S^2 and 1/S^2 stay finite
-    return exp2f((float)e);
+    return e > 40 ? 40 : (e < -40 ? -40 : e);  // S^2 and 1/S^2 stay finite
 }
 
 // ---------------------------------------------------------------------------------------------------
 // prep: row table (one 16-byte entry per schedule slot), zero rows without entries, and the maxima
 // that fix the FP16 scale.
 // ---------------------------------------------------------------------------------------------------
-__global__ void tc_prep_rows_kernel(HalfStepParams p, RowEnt* __restrict__ tab) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per schedule slot: row table entry, per-row FP16 scale, zero fill of rows without entries
+__global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, const float* __restrict__ hdr) {
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (s >= p.sched_len) return;
     const int64_t row = p.row_order ? p.row_order[s] : s;
-    RowEnt e{-1, 0, 0};
+    int4 e = make_int4(-1, 0, 0, 0);
     if (row >= 0) {
         const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-        e.row = (int32_t)row;
-        e.n = (int32_t)(hi - lo);
-        e.lo = lo;
-        if (hi == lo) {  // wmf_model.py:223-225
-            float* x = p.X + row * p.ldx;
-            for (int i = 0; i < F; ++i) x[i] = 0.0f;
-        }
-    }
-    tab[s] = e;
-}
-
-// out[0] = max diag(G) (block 0), out[1] = max |data[indptr[0] .. indptr[rows])|
-__global__ void tc_maxima_kernel(HalfStepParams p, uint32_t* __restrict__ out) {
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
         float m = 0.0f;
-        for (int i = threadIdx.x; i < F; i += 32) m = fmaxf(m, fabsf(p.G[i * F + i]));
+        for (int64_t i = lo + lane; i < hi; i += 32) m = fmaxf(m, fabsf(__ldg(p.data + i)));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (threadIdx.x == 0) atomicMax(out, __float_as_uint(m));
+        const int sexp = gram_scale_exp(hdr[2], m);
+        e.x = (int32_t)row;
+        e.y = (int32_t)(hi - lo);
+        e.z = (int32_t)(uint32_t)lo;
+        e.w = (int32_t)((uint32_t)((lo >> 32) & 0xFFFF) | ((uint32_t)(sexp + 64) << 16));
+        if (hi == lo) {  // wmf_model.py:223-225
+            float4* x = reinterpret_cast<float4*>(p.X + row * p.ldx);
+            if ((p.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0) x[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (int i = lane; i < F; i += 32) p.X[row * p.ldx + i] = 0.0f;
+        }
     }
-    const int64_t lo = p.indptr[0], hi = p.indptr[p.rows];
+    if (lane == 0) tab[s] = e;
+}
+
+// hdr[2] = max diag(G)
+__global__ void tc_maxima_kernel(HalfStepParams p, float* __restrict__ hdr) {
     float m = 0.0f;
-    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(p.data[i]));
+    for (int i = threadIdx.x; i < F; i += 32) m = fmaxf(m, fabsf(p.G[i * F + i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out + 1, __float_as_uint(m));  // order-preserving for m >= 0
+    if (threadIdx.x == 0) hdr[2] = m;
 }
 
 }  // namespace tc
@@ -262,8 +264,7 @@ using namespace tc;
 
 template <bool PROF>
 __global__ void __launch_bounds__(THREADS, 1)
-als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, const float* __restrict__ hdr,
-                        int* __restrict__ flags) {
+als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* __restrict__ flags) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = smem_base + OFF_BARS;
@@ -308,17 +309,17 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
 
     // slot k of this CTA = schedule slot k * gridDim + blockIdx
     const int nslots = (int)((p.sched_len - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const RowEnt* mytab = rowtab + blockIdx.x;
+    const int4* mytab = rowtab + blockIdx.x;
     const int64_t tstep = gridDim.x;
     auto ent_at = [&](int k) -> RowEnt {
-        RowEnt e{-1, 0, 0};
+        RowEnt e{-1, 0, 0, 0};
         if (k < nslots) {
-            const int4 v = __ldg(reinterpret_cast<const int4*>(mytab + (int64_t)k * tstep));
-            e.row = v.x; e.n = v.y; e.lo = ((int64_t)(uint32_t)v.z) | ((int64_t)v.w << 32);
+            const int4 v = __ldg(mytab + (int64_t)k * tstep);
+            e.row = v.x; e.n = v.y; e.lo = ((int64_t)(uint32_t)v.z) | ((int64_t)(v.w & 0xFFFF) << 32);
+            e.sexp = (int)((uint32_t)v.w >> 16) - 64;
         }
         return e;
     };
-    const float S = gram_scale(hdr);
 
     if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
         // =============================== GATHER ===============================
@@ -333,6 +334,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         int cu_row_n = -1;    // index of the row among this CTA's non-empty rows
         int cu_c = 0, cu_nsub = 0, cu_n = 0, cu_gi0 = 0;  // sub-chunk in row, sub-chunks / entries of the row, global index of sub-chunk 0
         int64_t cu_lo = 0;    // first entry of the row
+        float cu_S = 1.0f;    // FP16 scale of the row
         RowEnt w0 = ent_at(0), w1 = ent_at(1);  // prefetched table entries k+1, k+2
         auto advance = [&](bool first) {  // to the team's next sub-chunk
             if (!first) cu_c += 2;
@@ -347,7 +349,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                     if (e.n > 0) {
                         cu_gi0 += cu_nsub;
                         ++cu_row_n;
-                        cu_n = e.n; cu_lo = e.lo; cu_nsub = (e.n + SUB - 1) / SUB;
+                        cu_n = e.n; cu_lo = e.lo; cu_nsub = (e.n + SUB - 1) / SUB; cu_S = exp2f((float)e.sexp);
                         found = true;
                     }
                 }
@@ -364,10 +366,10 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             if (cu_k >= nslots) return Desc{-1, 0, false};
             return Desc{cu_gi0 + cu_c, cu_row_n, cu_c + 2 >= cu_nsub};
         };
-        struct Raw { int idx; float d; };
+        struct Raw { int idx; float d; float s; };
         bool saw_negative = false;
         auto load_raw = [&]() {  // lane l < 8 of warp w: entry 8w + l of the cursor's sub-chunk
-            Raw rw{-1, 0.f};
+            Raw rw{-1, 0.f, cu_S};
             if (cu_k < nslots && lane < 8) {
                 const int off = cu_c * SUB + gw * 8 + lane;
                 if (off < cu_n) { rw.d = __ldg(p.data + cu_lo + off); rw.idx = __ldg(p.indices + cu_lo + off); }
@@ -380,7 +382,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
                 float sq = 0.f, dp1 = 0.f;
                 if (rw.idx >= 0) {
                     if (rw.d < 0.f) saw_negative = true;
-                    sq = S * sqrtf(fabsf(rw.d));
+                    sq = rw.s * sqrtf(fabsf(rw.d));
                     dp1 = __fadd_rn(rw.d, 1.0f);
                 }
                 const uint32_t ma = smem_base + OFF_META + tb * META_BYTES + (gw * 8 + lane) * 4;
@@ -537,7 +539,6 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
         const float* Gcol = p.G + t;  // G is symmetric: G[t][c] = G[c][t], and column t is coalesced across the warp
-        const float inv_s = 1.0f / S, inv_s2 = inv_s * inv_s;  // exact: S is a power of two
         uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
@@ -551,6 +552,7 @@ als_half_step_tc_kernel(HalfStepParams p, const RowEnt* __restrict__ rowtab, con
             if ((int)(rn % NGROUP) != g) continue;
             ++my_rows;
             float* xout = p.X + (int64_t)e.row * p.ldx;
+            const float S = exp2f((float)e.sexp), inv_s = exp2f((float)-e.sexp), inv_s2 = inv_s * inv_s;  // exact powers of two
             if (prof) tt = clock64();
             // rhs partials: the team that owns sub-chunk 0 always delivers, the other one if the row has two or more
             const int t0 = rn & 1;
@@ -749,12 +751,12 @@ bool tc_half_step_supported(int f, int bias) { return f == tc::F && !bias; }
 // The public query only knows `rows`: schedules of up to 2*rows + 4096 slots fit.
 size_t tc_half_step_workspace_bytes(int64_t rows, int f, int) {
     const size_t a = simt_half_step_workspace_bytes(f);
-    const size_t b = WS_ROWTAB + sizeof(RowEnt) * (size_t)(2 * rows + 4096);
+    const size_t b = WS_ROWTAB + 16 * (size_t)(2 * rows + 4096);
     return a > b ? a : b;
 }
 
 int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st) {
-    const size_t need = WS_ROWTAB + sizeof(RowEnt) * (size_t)in.sched_len;
+    const size_t need = WS_ROWTAB + 16 * (size_t)in.sched_len;
     if (ws == nullptr || ws_bytes < need || ws_bytes < simt_half_step_workspace_bytes(in.f)) {
         set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu (schedule of %lld slots)", ws_bytes, need,
                   (long long)in.sched_len);
@@ -763,8 +765,8 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     WMF_CUDA(cudaMemsetAsync(ws, 0, WS_ROWTAB, st));
     char* base = reinterpret_cast<char*>(ws);
     int* flags = reinterpret_cast<int*>(base) + 1;  // [0] = SIMT row counter, [1] = redo flags
-    uint32_t* maxes = reinterpret_cast<uint32_t*>(base) + 2;
-    RowEnt* tab = reinterpret_cast<RowEnt*>(base + WS_ROWTAB);
+    float* hdr = reinterpret_cast<float*>(base);
+    int4* tab = reinterpret_cast<int4*>(base + WS_ROWTAB);
     static bool attr_set = false;
     if (!attr_set) {
         WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -775,15 +777,14 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     p.KC = getenv("WMF_TC_DEBUG") ? atoi(getenv("WMF_TC_DEBUG")) : 0;  // debug: 1 = output the rhs, 2+c = output column c of A
     p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
     const int sms = sm_count();
-    tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 255) / 256), 256, 0, st>>>(p, tab);
-    WMF_LAUNCH_CHECK("tc_prep_rows_kernel");
-    tc_maxima_kernel<<<sms * 4, 256, 0, st>>>(p, maxes);
+    tc_maxima_kernel<<<1, 32, 0, st>>>(p, hdr);
     WMF_LAUNCH_CHECK("tc_maxima_kernel");
+    tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, hdr);
+    WMF_LAUNCH_CHECK("tc_prep_rows_kernel");
     int grid = sms;
     if ((int64_t)grid > in.sched_len) grid = (int)in.sched_len;
-    const float* hdr = reinterpret_cast<const float*>(base);
-    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, hdr, flags);
-    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, hdr, flags);
+    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, flags);
+    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, flags);
     WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
     // fix-up: runs the FP32/LU kernel over the whole half-step only if a flag was raised
     HalfStepParams fix = in;
