@@ -53,7 +53,8 @@ constexpr int NSTG = 3;              // raw staging buffers per team (cp.async d
 constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 64 fp16 (K) = 16 KB, holds two sub-chunks
 constexpr int PAIR_BYTES = 2 * TILE_BYTES;   // [zh ; zl]
 constexpr int STG_BYTES = SUB * F * 4;       // 32 gathered factor rows, row-major fp32, 16 KB
-constexpr int META_BYTES = SUB * 8;          // S*sqrt(d) [32] then d+1 [32]
+constexpr int META_BYTES = SUB * 8;          // S*sqrt(d) [32] then d+1 [32], one copy per gather warp and buffer
+constexpr int WSTG_BYTES = SUB * 32 * 4;     // a gather warp's slice of a staging buffer: 32 entries x 32 features
 constexpr int NB = 8;                // Gauss-Jordan step width
 constexpr int NGROUP = 4;            // solver groups = TMEM accumulators
 constexpr int GROUP = 128;
@@ -77,7 +78,7 @@ constexpr int GROUP_BYTES = ((G_OFF_BFIN + F * 4 + 127) / 128) * 128;
 constexpr int OFF_STAGES = 0;                                        // NSTAGE/2 tile pairs
 constexpr int OFF_STG = OFF_STAGES + (NSTAGE / 2) * PAIR_BYTES;
 constexpr int OFF_META = OFF_STG + NTEAM * NSTG * STG_BYTES;
-constexpr int OFF_GROUPS = ((OFF_META + NTEAM * NSTG * META_BYTES + 127) / 128) * 128;
+constexpr int OFF_GROUPS = ((OFF_META + NTEAM * 4 * NSTG * META_BYTES + 127) / 128) * 128;
 constexpr int OFF_BVEC = OFF_GROUPS + NGROUP * GROUP_BYTES;         // NGROUP x NTEAM x F floats
 constexpr int OFF_BARS = OFF_BVEC + NGROUP * NTEAM * F * 4;         // mbarriers (8 B each)
 constexpr int NBARS = 2 * NSTAGE + NTEAM * NSTG + 2 + (4 + NTEAM) * NGROUP;
@@ -366,37 +367,43 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
             if (cu_k >= nslots) return Desc{-1, 0, false};
             return Desc{cu_gi0 + cu_c, cu_row_n, cu_c + 2 >= cu_nsub};
         };
+        // Every gather warp is its own pipeline: it stages the 32-feature slice (128 B) of the 32 factor rows that
+        // its lanes will read, so nothing but the operand-stage barriers is shared inside a team.
         struct Raw { int idx; float d; float s; };
         bool saw_negative = false;
-        auto load_raw = [&]() {  // lane l < 8 of warp w: entry 8w + l of the cursor's sub-chunk
+        const int wbuf0 = ((team * 4 + gw) * NSTG);  // this warp's first staging / meta buffer
+        auto load_raw = [&]() {  // lane l: entry l of the cursor's sub-chunk
             Raw rw{-1, 0.f, cu_S};
-            if (cu_k < nslots && lane < 8) {
-                const int off = cu_c * SUB + gw * 8 + lane;
+            if (cu_k < nslots) {
+                const int off = cu_c * SUB + lane;
                 if (off < cu_n) { rw.d = __ldg(p.data + cu_lo + off); rw.idx = __ldg(p.indices + cu_lo + off); }
             }
             return rw;
         };
         auto issue = [&](const Raw& rw, int buf) {
-            const int tb = team * NSTG + buf;
-            if (lane < 8) {
+            const int wb = wbuf0 + buf;
+            __syncwarp();  // the buffer's previous contents have been read by every lane
+            {
                 float sq = 0.f, dp1 = 0.f;
                 if (rw.idx >= 0) {
                     if (rw.d < 0.f) saw_negative = true;
                     sq = rw.s * sqrtf(fabsf(rw.d));
                     dp1 = __fadd_rn(rw.d, 1.0f);
                 }
-                const uint32_t ma = smem_base + OFF_META + tb * META_BYTES + (gw * 8 + lane) * 4;
+                const uint32_t ma = smem_base + OFF_META + wb * META_BYTES + lane * 4;
                 sts1(ma, sq);
                 sts1(ma + SUB * 4, dp1);
             }
-            const uint32_t dst0 = smem_base + OFF_STG + tb * STG_BYTES + (gw * 8) * (F * 4) + lane * 16;
+            // one instruction copies the 128-B slices of four entries: lanes 8k..8k+7 take entry 4i + k
+            const uint32_t dst0 = smem_base + OFF_STG + wb * WSTG_BYTES + (lane >> 3) * 128 + (lane & 7) * 16;
+            const int64_t col = gw * 32 + (lane & 7) * 4;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const int idx = __shfl_sync(0xffffffffu, rw.idx, jj);
-                const float* src = p.Y + (int64_t)(idx >= 0 ? idx : 0) * p.ldy + lane * 4;
-                cp_async16(dst0 + jj * (F * 4), src, idx >= 0 ? 16u : 0u);  // size 0 -> zero fill
+            for (int i = 0; i < 8; ++i) {
+                const int idx = __shfl_sync(0xffffffffu, rw.idx, 4 * i + (lane >> 3));
+                const float* src = p.Y + (int64_t)(idx >= 0 ? idx : 0) * p.ldy + col;
+                cp_async16(dst0 + i * 512, src, idx >= 0 ? 16u : 0u);  // size 0 -> zero fill
             }
-            cp_async_arrive(bar_stg(team, buf));
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
         advance(true);
         Desc d0 = describe();
@@ -408,26 +415,25 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
         Desc d2 = describe();
         Raw r2 = load_raw();
         advance(false);
-        uint32_t j = 0;
+        uint32_t j = 0;  // in iteration j the groups of sub-chunks j, j+1, j+2 are in flight: wait_group 2 completes j
         double bacc = 0.0;
         const bool prof = PROF && blockIdx.x == 0 && m == 0 && team == 0;
         long long t_empty = 0, t_bempty = 0, t_stg = 0, t_issue = 0, t_xform = 0, t_start = prof ? clock64() : 0, tt = 0, t2 = 0;
         while (d0.gi >= 0) {
             if (prof) t2 = clock64();
-            // buffer (j+2)%3 was read by every thread of the team during iteration j-1: barrier before refilling it
-            named_bar(1 + NGROUP + team, TEAM);
             const Desc d3 = describe();
             issue(r2, (j + 2) % NSTG);   // sub-chunk j+2
             r2 = load_raw();             // sub-chunk j+3, first touched next iteration
             advance(false);
             const int s = d0.gi % NSTAGE, sb = j % NSTG;
             if (prof) { tt = clock64(); t_issue += tt - t2; }
-            mbar_wait(bar_stg(team, sb), (j / NSTG) & 1u);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");  // this warp's copies for sub-chunk j have landed
+            __syncwarp();
             if (prof) { t2 = clock64(); t_stg += t2 - tt; }
             mbar_wait(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
             if (prof) { tt = clock64(); t_empty += tt - t2; }
-            const uint32_t stg = smem_base + OFF_STG + (team * NSTG + sb) * STG_BYTES + m * 4;
-            const uint32_t mt = smem_base + OFF_META + (team * NSTG + sb) * META_BYTES;
+            const uint32_t stg = smem_base + OFF_STG + (wbuf0 + sb) * WSTG_BYTES + lane * 4;
+            const uint32_t mt = smem_base + OFF_META + (wbuf0 + sb) * META_BYTES;
             const uint32_t tile_h = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + m * 128;
             const int half = s & 1;
             float part = 0.f;
@@ -440,8 +446,8 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
                 uint32_t hh[4], ll[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float v0 = lds1(stg + (c * 8 + 2 * e) * (F * 4));
-                    const float v1 = lds1(stg + (c * 8 + 2 * e + 1) * (F * 4));
+                    const float v0 = lds1(stg + (c * 8 + 2 * e) * 128);
+                    const float v1 = lds1(stg + (c * 8 + 2 * e + 1) * 128);
                     const float z0 = sq[2 * e] * v0, z1 = sq[2 * e + 1] * v1;
                     part = fmaf(dp[2 * e], v0, part);
                     part = fmaf(dp[2 * e + 1], v1, part);
@@ -477,7 +483,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
     } else if (warp == MMA_WARP) {
         // =============================== GRAM MMA ISSUE ===============================
         if (lane == 0) {
-            uint32_t gi = 0, row_n = 0, ks = 0;
+            uint32_t gi = 0, row_n = 0;
             const bool prof = PROF && blockIdx.x == 0;
             long long t_full = 0, t_accempty = 0, t_thr = 0, t_start = prof ? clock64() : 0, tt = 0;
             RowEnt nxt = ent_at(0);
@@ -503,19 +509,18 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
                     const int nk = (kc + 15) >> 4;
                     const uint32_t tile = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + (s & 1) * 64;
                     const uint64_t dh = umma_desc(tile), dl = umma_desc(tile + TILE_BYTES);
-                    for (int kk = 0; kk < nk; ++kk, ++ks) {
-                        if (ks >= 2) {  // at most two K-steps queued ahead of the solvers' updates
-                            if (prof) tt = clock64();
-                            mbar_wait(bar_thr(ks & 1), ((ks >> 1) - 1) & 1u);
-                            if (prof) t_thr += clock64() - tt;
-                        }
+                    if (gi >= 2) {  // at most two sub-chunks (12 MMAs) queued ahead of the solvers' updates
+                        if (prof) tt = clock64();
+                        mbar_wait(bar_empty((gi - 2) % NSTAGE), ((gi - 2) / NSTAGE) & 1u);
+                        if (prof) t_thr += clock64() - tt;
+                    }
+                    for (int kk = 0; kk < nk; ++kk) {
                         // advance 16 fp16 = 32 B along K inside the 128-B swizzle row
                         const uint64_t hk = dh + (uint64_t)(kk * 2), lk = dl + (uint64_t)(kk * 2);
                         umma_f16(d_tmem, hk, hk, IDESC_F16_M128_N128, accumulate);  // zh zh^T
                         umma_f16(d_tmem, hk, lk, IDESC_F16_M128_N128, 1u);          // zh zl^T
                         umma_f16(d_tmem, lk, hk, IDESC_F16_M128_N128, 1u);          // zl zh^T
                         accumulate = 1;
-                        tc_commit(bar_thr(ks & 1));
                     }
                     tc_commit(bar_empty(s));
                 }
