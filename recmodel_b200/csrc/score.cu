@@ -8,7 +8,9 @@
 // for 4 users at a time from a shared-memory tile of item rows (8 independent accumulators
 // per user = NumPy's 8 strided partial sums, so the thread-serial order is the same order).
 // Selection: per-user radix select on order-preserving keys + bitonic sort of the winners.
+#include <stdlib.h>
 #include "common.cuh"
+#include "score.cuh"
 
 namespace wmf {
 
@@ -89,8 +91,10 @@ __global__ __launch_bounds__(SC_THREADS) void score_tile_kernel(const int64_t* _
                                                                 int ub, const int64_t* __restrict__ cand, int64_t ni,
                                                                 const float* __restrict__ U, int64_t ldu,
                                                                 const float* __restrict__ V, int64_t ldv, int f,
-                                                                int bias, float* __restrict__ S) {
+                                                                int bias, float* __restrict__ S,
+                                                                const int* __restrict__ run_if) {
     extern __shared__ __align__(16) float sm[];
+    if (run_if != nullptr && *run_if == 0) return;  // fix-up launch after the tensor-core path: nothing overflowed
     const int FS = f + 1 + ((f & 1) ? 0 : 0);  // row stride (floats); f+1 keeps rows on distinct banks
     float* sV = sm;                            // SC_THREADS x FS
     float* sU = sm + (size_t)SC_THREADS * FS;  // SC_USERS x FS
@@ -136,11 +140,6 @@ __global__ __launch_bounds__(SC_THREADS) void score_tile_kernel(const int64_t* _
     }
 }
 
-__device__ __forceinline__ uint32_t order_key(float x) {
-    uint32_t b = __float_as_uint(x);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // larger float -> larger key
-}
-
 constexpr int TK_THREADS = 256;
 constexpr int TK_MAX = 1024;  // largest topn this kernel sorts in shared memory
 
@@ -149,8 +148,10 @@ constexpr int TK_MAX = 1024;  // largest topn this kernel sorts in shared memory
 __global__ __launch_bounds__(TK_THREADS) void topk_rows_kernel(const float* __restrict__ S, int64_t ni, int topn,
                                                                const int64_t* __restrict__ cand,
                                                                int64_t* __restrict__ out_ids,
-                                                               float* __restrict__ out_scores) {
+                                                               float* __restrict__ out_scores,
+                                                               const int* __restrict__ run_if) {
     __shared__ unsigned hist[256];
+    if (run_if != nullptr && *run_if == 0) return;
     __shared__ unsigned long long keys[TK_MAX];
     __shared__ unsigned s_prefix, s_need, s_count, s_tie_base;
     __shared__ unsigned s_scan[TK_THREADS / 32];
@@ -261,7 +262,9 @@ extern "C" {
 size_t wmf_score_topk_workspace_bytes(int64_t nu, int64_t ni, int topn) {
     (void)topn;
     if (nu <= 0 || ni <= 0) return 0;
-    return (size_t)score_user_batch(nu, ni) * (size_t)ni * sizeof(float);
+    const size_t exact = align_up((size_t)score_user_batch(nu, ni) * (size_t)ni * sizeof(float), 1024);
+    const size_t tc = exact + score_tc_workspace_bytes(nu, ni);  // the query does not know f: assume the tensor-core path
+    return exact > tc ? exact : tc;
 }
 
 int wmf_score_topk(const int64_t* users, int64_t nu, const int64_t* cand, int64_t ni, const float* U, int64_t ldu,
@@ -287,13 +290,28 @@ int wmf_score_topk(const int64_t* users, int64_t nu, const int64_t* cand, int64_
     WMF_CUDA(cudaFuncSetAttribute(score_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ubatch = score_user_batch(nu, ni);
     float* S = (float*)ws;
+    const size_t exact_bytes = align_up((size_t)ubatch * (size_t)ni * sizeof(float), 1024);
+    // Tensor-core candidate generation + exact rescoring when the shape allows it (WMF_SCORE_EXACT=1 forces
+    // the exact CUDA-core kernels); afterwards the exact kernels run only if a user overflowed its candidate list.
+    const bool use_tc = score_tc_supported(ni, f, bias, topn) && getenv("WMF_SCORE_EXACT") == nullptr &&
+                        ws_bytes >= exact_bytes + score_tc_workspace_bytes(nu, ni);
+    int* redo = nullptr;
+    if (use_tc) {
+        const int64_t tb = score_tc_user_batch(nu);
+        for (int64_t u0 = 0; u0 < nu; u0 += tb) {
+            const int ub = (int)((nu - u0) < tb ? (nu - u0) : tb);
+            int rc = score_topk_tc_batch(users, u0, ub, tb, cand, ni, U, ldu, V, ldv, f, bias, topn, out_ids, out_scores,
+                                         (char*)ws + exact_bytes, u0 == 0, &redo, st);
+            if (rc) return rc;
+        }
+    }
     for (int64_t u0 = 0; u0 < nu; u0 += ubatch) {
         const int ub = (int)((nu - u0) < ubatch ? (nu - u0) : ubatch);
         dim3 grid((unsigned)((ni + SC_THREADS - 1) / SC_THREADS), (unsigned)((ub + SC_USERS - 1) / SC_USERS));
-        score_tile_kernel<<<grid, SC_THREADS, smem, st>>>(users, u0, ub, cand, ni, U, ldu, V, ldv, f, bias, S);
+        score_tile_kernel<<<grid, SC_THREADS, smem, st>>>(users, u0, ub, cand, ni, U, ldu, V, ldv, f, bias, S, redo);
         WMF_LAUNCH_CHECK("score_tile_kernel");
         topk_rows_kernel<<<ub, TK_THREADS, 0, st>>>(S, ni, topn, cand, out_ids + (size_t)u0 * topn,
-                                                    out_scores ? out_scores + (size_t)u0 * topn : nullptr);
+                                                    out_scores ? out_scores + (size_t)u0 * topn : nullptr, redo);
         WMF_LAUNCH_CHECK("topk_rows_kernel");
     }
     return WMF_OK;
