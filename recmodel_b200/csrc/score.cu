@@ -99,8 +99,12 @@ __global__ __launch_bounds__(SC_THREADS) void score_tile_kernel(const int64_t* _
     float* sV = sm;                            // SC_THREADS x FS
     float* sU = sm + (size_t)SC_THREADS * FS;  // SC_USERS x FS
     const int tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * SC_THREADS;
-    const int u_tile0 = blockIdx.y * SC_USERS;
+    const int64_t tiles_x = (ni + SC_THREADS - 1) / SC_THREADS, tiles_y = (ub + SC_USERS - 1) / SC_USERS;
+    // grid-stride over (item tile, user tile): a conditional fix-up launch that has nothing to do exits cheaply
+    for (int64_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int64_t i0 = (tile % tiles_x) * SC_THREADS;
+    const int u_tile0 = (int)(tile / tiles_x) * SC_USERS;
+    __syncthreads();  // the previous tile's shared-memory rows have been consumed
     // stage item rows (coalesced: consecutive threads read consecutive columns of one row)
     for (int r = 0; r < SC_THREADS; ++r) {
         const int64_t ip = i0 + r;
@@ -116,7 +120,7 @@ __global__ __launch_bounds__(SC_THREADS) void score_tile_kernel(const int64_t* _
     }
     __syncthreads();
     const int64_t item_pos = i0 + tid;
-    if (item_pos >= ni) return;
+    if (item_pos >= ni) continue;
     const float* v = sV + (size_t)tid * FS;
     const int off = bias ? 1 : 0;
     for (int g = 0; g < SC_USERS / 4; ++g) {
@@ -137,6 +141,7 @@ __global__ __launch_bounds__(SC_THREADS) void score_tile_kernel(const int64_t* _
                 S[(size_t)(ul + q) * ni + item_pos] = s;
             }
         }
+    }
     }
 }
 
@@ -305,9 +310,19 @@ int wmf_score_topk(const int64_t* users, int64_t nu, const int64_t* cand, int64_
             if (rc) return rc;
         }
     }
-    for (int64_t u0 = 0; u0 < nu; u0 += ubatch) {
-        const int ub = (int)((nu - u0) < ubatch ? (nu - u0) : ubatch);
-        dim3 grid((unsigned)((ni + SC_THREADS - 1) / SC_THREADS), (unsigned)((ub + SC_USERS - 1) / SC_USERS));
+    int64_t xbatch = ubatch;
+    if (use_tc) {  // conditional fix-up after the tensor-core path: few large batches in its dead scratch regions
+        size_t off = 0, bytes = 0;
+        score_tc_fixup_region(nu, ni, &off, &bytes);
+        int64_t xb = (int64_t)(bytes / ((size_t)ni * sizeof(float))) / SC_USERS * SC_USERS;
+        if (xb > 65535ll * SC_USERS) xb = 65535ll * SC_USERS;
+        if (xb > ubatch) { xbatch = xb; S = (float*)((char*)ws + exact_bytes + off); }
+    }
+    for (int64_t u0 = 0; u0 < nu; u0 += xbatch) {
+        const int ub = (int)((nu - u0) < xbatch ? (nu - u0) : xbatch);
+        const int64_t tiles = ((ni + SC_THREADS - 1) / SC_THREADS) * ((ub + SC_USERS - 1) / SC_USERS);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
         score_tile_kernel<<<grid, SC_THREADS, smem, st>>>(users, u0, ub, cand, ni, U, ldu, V, ldv, f, bias, S, redo);
         WMF_LAUNCH_CHECK("score_tile_kernel");
         topk_rows_kernel<<<ub, TK_THREADS, 0, st>>>(S, ni, topn, cand, out_ids + (size_t)u0 * topn,

@@ -252,6 +252,7 @@ stc_gemm_kernel(const uint8_t* __restrict__ a_tiles, const uint8_t* __restrict__
         const bool live = u < ub;
         const int n_sub = n_item_tiles * (TN / SUB);
         float my_thr = 0.0f;
+        int my_cnt = 0;  // this thread is the only writer of its user's candidate list: no atomics
         if (MODE == 1 && live) my_thr = thr[u];
         for (int it = 0; it < n_item_tiles; ++it) {
             const int acc = it & 1;
@@ -275,18 +276,22 @@ stc_gemm_kernel(const uint8_t* __restrict__ a_tiles, const uint8_t* __restrict__
                     }
                     if (live) maxima[u * n_sub + it * (TN / SUB) + c] = m;
                 } else if (live) {
+                    uint32_t hits = 0;  // branch-free compare, then only the (rare) hits take the store path
 #pragma unroll
-                    for (int j = 0; j < SUB; ++j) {
-                        if (__uint_as_float(r[j]) >= my_thr && col0 + j < ni) {
-                            const int slot = atomicAdd(cnt + u, 1);
-                            if (slot < CAND_MAX) lists[u * CAND_MAX + slot] = (uint32_t)(col0 + j);
-                        }
+                    for (int j = 0; j < SUB; ++j) hits |= (__uint_as_float(r[j]) >= my_thr ? 1u : 0u) << j;
+                    if (col0 + SUB > ni) hits &= (col0 < ni) ? (0xFFFFFFFFu >> (32 - (int)(ni - col0))) : 0u;  // padding items
+                    while (hits) {
+                        const int j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        if (my_cnt < CAND_MAX) lists[u * CAND_MAX + my_cnt] = (uint32_t)(col0 + j);
+                        ++my_cnt;
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(bar_accempty(acc));
         }
+        if (MODE == 1 && live) cnt[u] = my_cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -352,6 +357,7 @@ __global__ __launch_bounds__(TK_THREADS) void stc_rescore_kernel(
     const float* __restrict__ V, int64_t ldv, int f, int bias, int64_t* __restrict__ out_ids,
     float* __restrict__ out_scores, int* __restrict__ overflow) {
     __shared__ unsigned long long keys[CAND_MAX];
+    __shared__ float su[K + 1];
     const int tid = threadIdx.x, lane = tid & 31;
     const int n_cand = cnt[blockIdx.x];
     if (n_cand > CAND_MAX || n_cand < topn) {  // too many near-ties for the candidate buffer: the exact path redoes the call
@@ -360,7 +366,10 @@ __global__ __launch_bounds__(TK_THREADS) void stc_rescore_kernel(
     }
     const uint32_t* cpos = lists + (size_t)blockIdx.x * CAND_MAX;
     // exact NumPy-order scores of the candidates (8 lanes per dot product)
-    const float* u = U + users[u_begin + blockIdx.x] * ldu;
+    const float* ug = U + users[u_begin + blockIdx.x] * ldu;
+    for (int i = tid; i < f; i += TK_THREADS) su[i] = ug[i];
+    __syncthreads();
+    const float* u = su;
     const int gl = lane & 7;
     const unsigned gmask = 0xFFu << (lane & 24);
     for (int c0 = 0; c0 < n_cand; c0 += TK_THREADS / 8) {
@@ -368,7 +377,23 @@ __global__ __launch_bounds__(TK_THREADS) void stc_rescore_kernel(
         const bool ok = c < n_cand;
         const uint32_t pos = cpos[ok ? c : 0];
         const float* v = V + (cand ? cand[pos] : (int64_t)pos) * ldv;
-        const float sc = np_score(u, v, f, bias, gl, gmask);
+        float sc;
+        if (f == 128 && !bias) {
+            // np_block_sum for n = 128 with the 16 loads of this lane in flight together: accumulator gl takes
+            // p[8b + gl], b = 0..15 in order, then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) (wmf_model.py:206)
+            float vv[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) vv[b] = __ldg(v + 8 * b + gl);
+            float r = __fmul_rn(u[gl], vv[0]);
+#pragma unroll
+            for (int b = 1; b < 16; ++b) r = __fadd_rn(r, __fmul_rn(u[8 * b + gl], vv[b]));
+            r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+            r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+            r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+            sc = r;
+        } else {
+            sc = np_score(u, v, f, bias, gl, gmask);
+        }
         if (ok && gl == 0) keys[c] = ((unsigned long long)order_key(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - pos);
     }
     int npow = 1;
@@ -436,6 +461,14 @@ static TcLayout tc_layout(int64_t ubatch, int64_t ni) {
 }
 
 size_t score_tc_workspace_bytes(int64_t nu, int64_t ni) { return tc_layout(score_tc_user_batch(nu), ni).total; }
+
+// the block-maxima and candidate-list regions are dead once the tensor-core path has run: the exact fix-up
+// (only executed after an overflow) uses them as its score tile
+void score_tc_fixup_region(int64_t nu, int64_t ni, size_t* offset, size_t* bytes) {
+    const TcLayout l = tc_layout(score_tc_user_batch(nu), ni);
+    *offset = l.off_max;
+    *bytes = l.total - l.off_max;
+}
 
 // One user batch of the tensor-core path; `ws` is the tensor-core part of the workspace. `overflow_flag`
 // (device int) tells the caller's conditional exact kernels whether to redo the call.

@@ -7,7 +7,7 @@ dev = torch.device("cuda:0")
 rng = np.random.default_rng(0)
 U = torch.from_numpy(rng.standard_normal((138493, 128)).astype(np.float32) * 0.1).to(dev)
 V = torch.from_numpy(rng.standard_normal((26744, 128)).astype(np.float32) * 0.1).to(dev)
-users = torch.arange(16384, device=dev, dtype=torch.int64)
+users = torch.arange(138493, device=dev, dtype=torch.int64)
 engine.score_topk(users, None, U, V, 100); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     engine.score_topk(users, None, U, V, 100); torch.cuda.synchronize()

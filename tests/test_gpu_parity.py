@@ -335,6 +335,43 @@ def test_rank_all_equal_scores_ties_by_position(cuda_device):
     np.testing.assert_array_equal(m.rank(np.arange(300), 0, 7), np.arange(7))
 
 
+@pytest.mark.parametrize("f,bias,ni,topn,shuffled", [(128, False, 26_744, 100, False), (65, True, 9000, 50, True),
+                                                     (32, False, 4096, 128, False), (127, True, 3000, 10, True)])
+def test_rank_tensor_core_path_equals_exact_path(cuda_device, monkeypatch, f, bias, ni, topn, shuffled):
+    """K4/K5: tcgen05 candidate generation + exact rescoring must return the exact path's lists, element for
+    element (same sets, same order, ties by candidate position). The exact path is the one the tests above pin
+    against the oracle; WMF_SCORE_EXACT=1 forces it."""
+    rng = np.random.default_rng(7 * ni + f)
+    nu = 300
+    scale = np.float32(10.0 ** rng.uniform(-3, 2))  # the power-of-two operand scaling must not matter
+    U = (rng.standard_normal((nu, f)) * scale).astype(np.float32)
+    V = (rng.standard_normal((ni, f)) * 0.3).astype(np.float32)
+    V[ni // 2] = V[ni // 3]                      # an exact tie
+    V[7] = 0                                     # a zero row
+    m = WMF(num_items=ni, num_users=nu, dim=f - 1 if bias else f, gamma=0.1, weighted=True, bias=bias)
+    m.users, m.items = U, V
+    cand = rng.permutation(ni)[: ni - 17] if shuffled else np.arange(ni)
+    assert _lib.load().wmf_score_topk_workspace_bytes(nu, len(cand), topn) > nu * len(cand) * 4  # tc scratch included
+    got = m.rank_batch(cand, np.arange(nu), topn)
+    monkeypatch.setenv("WMF_SCORE_EXACT", "1")
+    ref = m.rank_batch(cand, np.arange(nu), topn)
+    np.testing.assert_array_equal(got, ref)
+    for u in (0, 5, nu - 1):                      # and the exact path itself against the oracle
+        s = orc.rank_scores(U, V, cand, u, bias)
+        pos = {int(c): k for k, c in enumerate(cand)}
+        np.testing.assert_array_equal(np.sort(s[[pos[int(i)] for i in ref[u]]])[::-1], np.sort(s)[::-1][:topn])
+
+
+def test_rank_tensor_core_overflow_falls_back_to_exact(cuda_device):
+    """More than 1024 candidates within the error band (all scores equal): the flag makes the exact kernels
+    redo the call, ties by position."""
+    ni = 5000
+    m = WMF(num_items=ni, num_users=3, dim=16, gamma=0.1, weighted=True)
+    m.users, m.items = np.ones((3, 16), np.float32), np.ones((ni, 16), np.float32)
+    out = m.rank_batch(np.arange(ni), np.arange(3), 40)
+    np.testing.assert_array_equal(out, np.tile(np.arange(40), (3, 1)))
+
+
 # ------------------------------------------------------------------------------- R2, R11, R12
 @pytest.mark.parametrize("algo_name", ["simt", "tcgen05"])
 @pytest.mark.parametrize("name,dim,bias,mode", WEIGHTED_CASES)
