@@ -101,6 +101,9 @@ int wmf_predict_pairs(const int64_t* users, int64_t user_stride, const int64_t* 
 /* K4+K5. Top-N over a candidate list for a batch of users: replaces WMF.rank (:25-47).
  * Scores are the bit-exact fp32 scores of wmf_predict_pairs, so the selected index SET equals
  * the reference's; order is descending score, ties broken by lower candidate position.
+ * When f (+1 with bias) <= 128, ni >= 256 and topn <= min(512, ni/32) the candidates come from a
+ * tcgen05 FP16 GEMM with a proven error band and only they are rescored exactly (same lists as the
+ * all-exact path, which the environment variable WMF_SCORE_EXACT=1 forces).
  * cand (nullable) = int64 candidate item ids [ni] (null: items 0..ni-1). out_ids [nu*topn]
  * receives item ids, out_scores (nullable) their scores. */
 size_t wmf_score_topk_workspace_bytes(int64_t nu, int64_t ni, int topn);
