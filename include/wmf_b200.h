@@ -76,6 +76,10 @@ int wmf_gram(const float* Y, int64_t n, int f, int64_t ldy, float lambda, int on
 size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo);
 /* 1 if `algo` (WMF_ALGO_SIMT / WMF_ALGO_TCGEN05) handles factor width f with/without bias, else 0. */
 int wmf_als_half_step_supports(int algo, int f, int bias);
+/* The tcgen05 path cuts rows with more stored entries than this into segments that different CTAs
+ * accumulate (partial Grams summed in segment order before the solve: a function of the row alone, so
+ * sharding never changes a row's arithmetic). A schedule should cost such a row as that many entries. */
+int wmf_als_row_split_entries(void);
 int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data,
                       int64_t rows, const int32_t* row_order, int64_t order_len, const float* Y,
                       int64_t ldy, int f,

@@ -10,7 +10,11 @@ static int resolve_algo(int algo, int f, int bias) {
     return algo;
 }
 
+namespace wmf { int wmf_tc_split_length(); }
+
 extern "C" {
+
+int wmf_als_row_split_entries(void) { return wmf_tc_split_length(); }
 
 int wmf_als_half_step_supports(int algo, int f, int bias) {
     if (f <= 0 || f > WMF_MAX_F || (bias && f < 2)) return 0;

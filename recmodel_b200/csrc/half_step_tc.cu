@@ -87,14 +87,28 @@ constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                // + slack f
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_GROUPS % 128 == 0 && GROUP_BYTES % 128 == 0 && OFF_BARS % 8 == 0 && OFF_STG % 1024 == 0, "alignment");
 
-// workspace layout (bytes): [0] SIMT row counter, [4] redo flags, [8] max diag(G),
-// [256, 768) profile slots, [1024, ...) row table
-constexpr size_t WS_PROF = 256, WS_ROWTAB = 1024;
+// workspace layout (bytes): [0] SIMT row counter, [4] redo flags, [8] max diag(G), [16] total slots,
+// [20] split rows, [24] partial slots, [28] extra slots, [256, 768) profile slots, [1024, ...) split-row
+// counters, row table, partial-Gram scratch
+constexpr size_t WS_PROF = 256, WS_COUNTERS = 1024;
+constexpr int SPLIT_LEN = 8192;      // rows longer than this are cut into segments of at most this many entries
+constexpr int MAX_SPLIT_ROWS = 4096; // split rows per call (more: the rest stay whole)
+constexpr int MAX_PARTS = 2048;      // segments of split rows per call = partial-Gram scratch slots
+constexpr size_t WS_ROWTAB = WS_COUNTERS + MAX_SPLIT_ROWS * 4;
+constexpr size_t PART_FLOATS = (size_t)F * F + F;  // a segment's S^2 W (chunk-major) and its rhs partial
 struct __align__(16) RowEnt {
     int32_t row;   // CSR row id, -1 = padding slot
     int32_t n;     // stored entries (0: nothing to do, X row already zeroed)
     int64_t lo;    // indptr[row] (48 bits when packed in the table)
-    int32_t sexp;  // S = 2^sexp for this row (the table packs it into the top 16 bits of lo)
+    int32_t sexp;  // S = 2^sexp for this row (the table packs it into bits 16-23 of the last word)
+    int32_t part;  // >= 0: this entry is a segment of a split row; index of its record in the split table (bits 24-31 flag)
+};
+// second table, one 16-byte record per segment of a split row
+struct __align__(16) SegEnt {
+    int32_t split_id;    // counter slot of the row
+    int32_t nseg;        // segments of the row
+    int32_t first_part;  // scratch slot of segment 0 (segments are consecutive)
+    int32_t seg;         // this segment's index
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,6 +189,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -223,8 +245,12 @@ __device__ __forceinline__ int gram_scale_exp(float max_diag_g, float max_d) {
 // prep: row table (one 16-byte entry per schedule slot), zero rows without entries, and the maxima
 // that fix the FP16 scale.
 // ---------------------------------------------------------------------------------------------------
-// one warp per schedule slot: row table entry, per-row FP16 scale, zero fill of rows without entries
-__global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, const float* __restrict__ hdr) {
+// One warp per schedule slot: row table entry, per-row FP16 scale, zero fill of rows without entries.
+// Rows longer than SPLIT_LEN are cut into equal segments (a function of the row length only, so a row's
+// arithmetic never depends on the launch it is in): segment 0 stays in the row's slot, the others go to
+// extra slots behind the schedule, which the persistent CTAs reach round-robin like every other slot.
+__global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, int4* __restrict__ segtab,
+                                    uint32_t* __restrict__ hdr_u, int64_t extra_slot0, int max_extra, int max_parts) {
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= p.sched_len) return;
@@ -232,22 +258,67 @@ __global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, co
     int4 e = make_int4(-1, 0, 0, 0);
     if (row >= 0) {
         const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
+        const int64_t n = hi - lo;
         float m = 0.0f;
         for (int64_t i = lo + lane; i < hi; i += 32) m = fmaxf(m, fabsf(__ldg(p.data + i)));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const int sexp = gram_scale_exp(hdr[2], m);
+        const int sexp = gram_scale_exp(__uint_as_float(hdr_u[2]), m);
+        const uint32_t sbits = (uint32_t)(sexp + 64) << 16;
+        // equal segments of whole sub-chunks, none empty (a function of the row length alone)
+        int nseg = 1;
+        int64_t seg_len = n;
+        if (n > SPLIT_LEN) {
+            const int64_t want = (n + SPLIT_LEN - 1) / SPLIT_LEN;
+            seg_len = ((n + want - 1) / want + SUB - 1) / SUB * SUB;
+            nseg = (int)((n + seg_len - 1) / seg_len);
+        }
+        int split_id = 0, first_part = 0, extra_base = 0;
+        if (nseg > 1) {
+            if (lane == 0) {
+                split_id = (int)atomicAdd(hdr_u + 5, 1u);
+                first_part = (int)atomicAdd(hdr_u + 6, (uint32_t)nseg);
+                extra_base = (int)atomicAdd(hdr_u + 7, (uint32_t)(nseg - 1));
+            }
+            split_id = __shfl_sync(0xffffffffu, split_id, 0);
+            first_part = __shfl_sync(0xffffffffu, first_part, 0);
+            extra_base = __shfl_sync(0xffffffffu, extra_base, 0);
+            if (split_id >= MAX_SPLIT_ROWS || first_part + nseg > max_parts || extra_base + nseg - 1 > max_extra)
+                nseg = 1;  // out of scratch: this row stays whole (slow, still correct)
+        }
         e.x = (int32_t)row;
-        e.y = (int32_t)(hi - lo);
-        e.z = (int32_t)(uint32_t)lo;
-        e.w = (int32_t)((uint32_t)((lo >> 32) & 0xFFFF) | ((uint32_t)(sexp + 64) << 16));
-        if (hi == lo) {  // wmf_model.py:223-225
-            float4* x = reinterpret_cast<float4*>(p.X + row * p.ldx);
-            if ((p.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0) x[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-            else for (int i = lane; i < F; i += 32) p.X[row * p.ldx + i] = 0.0f;
+        if (nseg == 1) {
+            e.y = (int32_t)n;
+            e.z = (int32_t)(uint32_t)lo;
+            e.w = (int32_t)((uint32_t)((lo >> 32) & 0xFFFF) | sbits);
+            if (n == 0) {  // wmf_model.py:223-225
+                float4* x = reinterpret_cast<float4*>(p.X + row * p.ldx);
+                if ((p.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0) x[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else for (int i = lane; i < F; i += 32) p.X[row * p.ldx + i] = 0.0f;
+            }
+        } else {
+            for (int k = lane; k < nseg; k += 32) {
+                const int64_t slo = lo + (int64_t)k * seg_len;
+                const int64_t shi = slo + seg_len < hi ? slo + seg_len : hi;
+                int4 se;
+                se.x = (int32_t)row;
+                se.y = (int32_t)(shi > slo ? shi - slo : 0);
+                se.z = (int32_t)(uint32_t)slo;
+                se.w = (int32_t)((uint32_t)((slo >> 32) & 0xFFFF) | sbits | 0x80000000u);  // bit 31: segment of a split row
+                const int64_t slot = k == 0 ? s : extra_slot0 + extra_base + (k - 1);
+                tab[slot] = se;
+                segtab[slot] = make_int4(split_id, nseg, first_part, k);
+            }
+            return;
         }
     }
     if (lane == 0) tab[s] = e;
+}
+
+// total slots = schedule (rounded up to a multiple of the grid) + extra segment slots
+__global__ void tc_finish_prep_kernel(uint32_t* __restrict__ hdr_u, int64_t extra_slot0, int max_extra) {
+    const uint32_t extra = hdr_u[7] < (uint32_t)max_extra ? hdr_u[7] : (uint32_t)max_extra;
+    hdr_u[4] = (uint32_t)(extra_slot0 + extra);
 }
 
 // hdr[2] = max diag(G)
@@ -265,7 +336,9 @@ using namespace tc;
 
 template <bool PROF>
 __global__ void __launch_bounds__(THREADS, 1)
-als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* __restrict__ flags) {
+als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const int4* __restrict__ segtab,
+                        float* __restrict__ parts, int* __restrict__ counters, const uint32_t* __restrict__ hdr_u,
+                        int* __restrict__ flags) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = smem_base + OFF_BARS;
@@ -309,15 +382,17 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
     // slot k of this CTA = schedule slot k * gridDim + blockIdx
-    const int nslots = (int)((p.sched_len - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int64_t total_slots = (int64_t)hdr_u[4];  // schedule + extra segment slots (set by the prep kernels)
+    const int nslots = (int)((total_slots - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int4* mytab = rowtab + blockIdx.x;
     const int64_t tstep = gridDim.x;
     auto ent_at = [&](int k) -> RowEnt {
-        RowEnt e{-1, 0, 0, 0};
+        RowEnt e{-1, 0, 0, 0, -1};
         if (k < nslots) {
             const int4 v = __ldg(mytab + (int64_t)k * tstep);
             e.row = v.x; e.n = v.y; e.lo = ((int64_t)(uint32_t)v.z) | ((int64_t)(v.w & 0xFFFF) << 32);
-            e.sexp = (int)((uint32_t)v.w >> 16) - 64;
+            e.sexp = (int)(((uint32_t)v.w >> 16) & 0xFFu) - 64;
+            e.part = (v.w < 0) ? k : -1;  // segment of a split row: its record sits at the same slot of the split table
         }
         return e;
     };
@@ -574,6 +649,50 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
             mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
             tc_fence_after();
             if (prof) { t_accfull += clock64() - tt; tt = clock64(); }
+            if (e.part >= 0) {
+                // ---- segment of a split row: park the partial S^2 W and rhs in the scratch; the segment that arrives
+                // last adds all of them in segment order (deterministic) and goes on to solve the row
+                const int4 sg = __ldg(segtab + (int64_t)e.part * tstep + blockIdx.x);  // split_id, nseg, first_part, seg
+                float* mine = parts + (size_t)(sg.z + sg.w) * PART_FLOATS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < F; c0 += NB) {
+                    float a[NB];
+                    tmem_ld8(t_row + c0, a);
+                    float4* dst = reinterpret_cast<float4*>(mine + (c0 >> 3) * (F * NB) + t * NB);
+                    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+                    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+                }
+                mine[F * F + t] = bt;
+                __threadfence();
+                named_bar(bar_id, GROUP);
+                if (t == 0) sts1(Dblk, __int_as_float(atomicAdd(counters + sg.x, 1) == sg.y - 1 ? 1 : 0));
+                named_bar(bar_id, GROUP);
+                const bool last = __float_as_int(lds1(Dblk)) != 0;
+                named_bar(bar_id, GROUP);  // Dblk is reused by the solve below
+                if (!last) {
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty(g));
+                    continue;
+                }
+                __threadfence();
+                const float* first = parts + (size_t)sg.z * PART_FLOATS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < F; c0 += NB) {
+                    float a[NB] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int k2 = 0; k2 < sg.y; ++k2) {
+                        const float4* src = reinterpret_cast<const float4*>(first + (size_t)k2 * PART_FLOATS + (c0 >> 3) * (F * NB) + t * NB);
+                        const float4 x0 = __ldcg(src), x1 = __ldcg(src + 1);
+                        a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
+                        a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
+                    }
+                    tmem_st8(t_row + c0, a);
+                }
+                bt = 0.0f;
+                for (int k2 = 0; k2 < sg.y; ++k2) bt += __ldcg(first + (size_t)k2 * PART_FLOATS + F * F + t);
+                tc_fence_before();
+                named_bar(bar_id, GROUP);
+                tc_fence_after();
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < F; c0 += NB) {
                 float gg[NB];
@@ -752,26 +871,44 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, int* 
 
 bool tc_half_step_supported(int f, int bias) { return f == tc::F && !bias; }
 
-// header + profile slots + one 16-byte row-table entry per schedule slot (f = 128 needs no SIMT slab).
-// The public query only knows `rows`: schedules of up to 2*rows + 4096 slots fit.
+// header, split-row counters, row table + split table (32 bytes per slot), partial-Gram scratch for the
+// segments of split rows (f = 128 needs no SIMT slab). The public query only knows `rows`: schedules of up
+// to 2*rows + 4096 slots fit; scratch for MAX_PARTS segments (128 for matrices with fewer than 1024 rows).
+static inline size_t tc_slot_bytes(size_t slots) { return slots * 32; }
 size_t tc_half_step_workspace_bytes(int64_t rows, int f, int) {
     const size_t a = simt_half_step_workspace_bytes(f);
-    const size_t b = WS_ROWTAB + 16 * (size_t)(2 * rows + 4096);
+    const size_t parts = rows >= 1024 ? (size_t)MAX_PARTS : 128;
+    const size_t b = WS_ROWTAB + tc_slot_bytes((size_t)(2 * rows + 4096 + 1024) + parts) + parts * PART_FLOATS * sizeof(float);
     return a > b ? a : b;
 }
 
+int wmf_tc_split_length() { return SPLIT_LEN; }
+
 int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st) {
-    const size_t need = WS_ROWTAB + 16 * (size_t)in.sched_len;
+    const int sms = sm_count();
+    int grid = sms;
+    if ((int64_t)grid > in.sched_len) grid = (int)in.sched_len;
+    const int64_t extra_slot0 = (in.sched_len + grid - 1) / grid * grid;
+    const size_t need = WS_ROWTAB + tc_slot_bytes((size_t)extra_slot0);
     if (ws == nullptr || ws_bytes < need || ws_bytes < simt_half_step_workspace_bytes(in.f)) {
         set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu (schedule of %lld slots)", ws_bytes, need,
                   (long long)in.sched_len);
         return WMF_ERR_WORKSPACE;
     }
-    WMF_CUDA(cudaMemsetAsync(ws, 0, WS_ROWTAB, st));
+    // whatever is left after the tables is scratch for segments of split rows (each needs a table slot too)
+    int64_t max_parts = (int64_t)((ws_bytes - need) / (PART_FLOATS * sizeof(float) + 32));
+    if (max_parts > MAX_PARTS) max_parts = MAX_PARTS;
+    if (max_parts < 2) max_parts = 0;
+    const int64_t cap_slots = extra_slot0 + max_parts;
     char* base = reinterpret_cast<char*>(ws);
     int* flags = reinterpret_cast<int*>(base) + 1;  // [0] = SIMT row counter, [1] = redo flags
     float* hdr = reinterpret_cast<float*>(base);
+    uint32_t* hdr_u = reinterpret_cast<uint32_t*>(base);
+    int* counters = reinterpret_cast<int*>(base + WS_COUNTERS);
     int4* tab = reinterpret_cast<int4*>(base + WS_ROWTAB);
+    int4* segtab = tab + cap_slots;
+    float* parts = reinterpret_cast<float*>(base + WS_ROWTAB + tc_slot_bytes((size_t)cap_slots));
+    WMF_CUDA(cudaMemsetAsync(ws, 0, WS_ROWTAB + (size_t)cap_slots * 16, st));  // header, counters, empty row table
     static bool attr_set = false;
     if (!attr_set) {
         WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -781,15 +918,15 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     HalfStepParams p = in;
     p.KC = getenv("WMF_TC_DEBUG") ? atoi(getenv("WMF_TC_DEBUG")) : 0;  // debug: 1 = output the rhs, 2+c = output column c of A
     p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
-    const int sms = sm_count();
     tc_maxima_kernel<<<1, 32, 0, st>>>(p, hdr);
     WMF_LAUNCH_CHECK("tc_maxima_kernel");
-    tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, hdr);
+    tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, segtab, hdr_u, extra_slot0,
+                                                                            (int)max_parts, (int)max_parts);
     WMF_LAUNCH_CHECK("tc_prep_rows_kernel");
-    int grid = sms;
-    if ((int64_t)grid > in.sched_len) grid = (int)in.sched_len;
-    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, flags);
-    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, flags);
+    tc_finish_prep_kernel<<<1, 1, 0, st>>>(hdr_u, extra_slot0, (int)max_parts);
+    WMF_LAUNCH_CHECK("tc_finish_prep_kernel");
+    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, flags);
+    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, flags);
     WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
     // fix-up: runs the FP32/LU kernel over the whole half-step only if a flag was raised
     HalfStepParams fix = in;

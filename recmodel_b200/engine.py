@@ -150,7 +150,7 @@ class DeviceCSR:
                                        shape=self.shape)
 
 
-def device_schedule(indptr, n_cta, chunk=32, row_overhead=4):
+def device_schedule(indptr, n_cta, chunk=32, row_overhead=4, split=None):
     """``balanced_schedule`` with the O(rows log rows) part on the device: the rows are sorted by
     length there; when no row is heavy (the common case) the padded sorted order IS the schedule
     and nothing but two scalars crosses to the host. With a heavy head only the sorted costs go to
@@ -159,6 +159,11 @@ def device_schedule(indptr, n_cta, chunk=32, row_overhead=4):
     rows = counts.numel()
     if rows == 0:
         return torch.full((n_cta,), -1, dtype=torch.int32, device=indptr.device)
+    if split is None:
+        split = int(_lib.load().wmf_als_row_split_entries())
+    # the kernel cuts longer rows into segments and spreads the extra segments over all CTAs: a row never
+    # costs its CTA more than one segment
+    counts = torch.clamp(counts, max=split)
     sorted_counts, order = torch.sort(counts, descending=True, stable=True)
     cost = torch.where(sorted_counts > 0, (sorted_counts + (chunk - 1)) // chunk + row_overhead,
                        torch.zeros_like(sorted_counts))

@@ -188,6 +188,41 @@ def test_half_step_indefinite_falls_back_to_lu(cuda_device, algo_name, algo):
     assert row_rel_err(X, x64) < max(tol, 1e-3)  # indefinite systems: conditioning-limited
 
 
+def test_half_step_split_rows(cuda_device):
+    """Rows longer than wmf_als_row_split_entries() are accumulated by several CTAs (tcgen05 path) and their
+    partial Grams summed in segment order: same accuracy bar, bitwise independent of the schedule and of
+    which other rows share the launch (row sharding)."""
+    f = 128
+    if not tc_supported(f, False):
+        pytest.skip("shape not taken by the tcgen05 path")
+    split = int(_lib.load().wmf_als_row_split_entries())
+    rng = np.random.default_rng(77)
+    N, R = 70_000, 1200
+    lens = rng.integers(0, 120, R)
+    lens[[3, 40, 41, 700, 1199]] = [6 * split + 5, split + 1, split, 2 * split + 1000, 3 * split]
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    indices = np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lens]).astype(np.int32)
+    data = orc.preprocess_counts(rng.integers(1, 6, indptr[-1]).astype(np.float32))
+    C = scipy.sparse.csr_matrix((data, indices, indptr), shape=(R, N))
+    Y = (rng.standard_normal((N, f)) * 0.2).astype(np.float32)
+    X, _ = run_half_step(Y, C, False, _lib.ALGO_TCGEN05, cuda_device)
+    assert np.all(np.isfinite(X))
+    check = np.array([3, 40, 41, 700, 1199, 0, 1, 2, 500])
+    ref = orc.half_step(Y, C[check], 0.1)
+    x64, tol = half_step_tol(Y, C[check], ref, False)
+    err = row_rel_err(X[check], x64)
+    print(f"split rows: gpu-vs-fp64 {err:.2e} (tol {tol:.2e})")
+    assert err < tol
+    Xs, _ = run_half_step(Y, C, False, _lib.ALGO_SIMT, cuda_device)
+    assert row_rel_err(X, Xs) < HALF_STEP_TOL
+    X2, _ = run_half_step(Y, C, False, _lib.ALGO_TCGEN05, cuda_device, use_row_order=False)
+    np.testing.assert_array_equal(X, X2)
+    Xa, _ = run_half_step(Y, C[:650], False, _lib.ALGO_TCGEN05, cuda_device)
+    np.testing.assert_array_equal(Xa, X[:650])
+    Xb, _ = run_half_step(Y, C[650:], False, _lib.ALGO_TCGEN05, cuda_device)
+    np.testing.assert_array_equal(Xb, X[650:])
+
+
 def test_half_step_full_size_properties(cuda_device):
     """Config 2 at full size (138 493 x 26 744, 20 M entries, f=128): size-independent checks.
     (1) normal-equation residual of sampled rows in fp64; (2) bitwise determinism;
