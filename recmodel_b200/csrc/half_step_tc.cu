@@ -746,19 +746,16 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                         bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
                         bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
                     }
-                    Factor8 fo;
-                    const bool ok = factor8(d, bb, fo);
-                    if (lane == 0) {  // published scaled: S N and zb / S, so P comes out as S P (the MMA operand) for free
+                    float ncol[NB], z[NB];
+                    const bool ok = factor8(d, bb, lane & 7, ncol, z);  // lane c holds column c of N = L^-1
+                    // published scaled: S N and z / S, so P comes out as S P (the MMA operand) for free
+                    if (lane < NB) {
 #pragma unroll
-                        for (int i = 0; i < NB; ++i) {
-                            sts4(nd + i * 32, S * fo.n[TRI(i, 0)], i >= 1 ? S * fo.n[TRI(i, 1)] : 0.f,
-                                 i >= 2 ? S * fo.n[TRI(i, 2)] : 0.f, i >= 3 ? S * fo.n[TRI(i, 3)] : 0.f);
-                            if (i >= 4)
-                                sts4(nd + i * 32 + 16, S * fo.n[TRI(i, 4)], i >= 5 ? S * fo.n[TRI(i, 5)] : 0.f,
-                                     i >= 6 ? S * fo.n[TRI(i, 6)] : 0.f, i >= 7 ? S * fo.n[TRI(i, 7)] : 0.f);
-                        }
-                        sts4(zd, inv_s * fo.zb[0], inv_s * fo.zb[1], inv_s * fo.zb[2], inv_s * fo.zb[3]);
-                        sts4(zd + 16, inv_s * fo.zb[4], inv_s * fo.zb[5], inv_s * fo.zb[6], inv_s * fo.zb[7]);
+                        for (int i = 0; i < NB; ++i) sts1(nd + i * 32 + lane * 4, S * ncol[i]);
+                    }
+                    if (lane == 0) {
+                        sts4(zd, inv_s * z[0], inv_s * z[1], inv_s * z[2], inv_s * z[3]);
+                        sts4(zd + 16, inv_s * z[4], inv_s * z[5], inv_s * z[6], inv_s * z[7]);
                         if (!ok) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
                     }
                     if (prof) { t4 = clock64(); ph_own += t4 - t3; }
