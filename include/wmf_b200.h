@@ -80,6 +80,11 @@ int wmf_als_half_step_supports(int algo, int f, int bias);
  * accumulate (partial Grams summed in segment order before the solve: a function of the row alone, so
  * sharding never changes a row's arithmetic). A schedule should cost such a row as that many entries. */
 int wmf_als_row_split_entries(void);
+/* Workspace for a call whose long rows make `segments` segments in total: a row of n > L =
+ * wmf_als_row_split_entries() stored entries makes at most ceil(n / L) of them. The plain query above
+ * provides scratch for 2048 segments; a call that runs out of scratch still returns correct results
+ * (the exact CUDA-core kernel redoes the half-step) but slowly. */
+size_t wmf_als_half_step_workspace_bytes_split(int64_t rows, int f, int algo, int64_t segments);
 int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data,
                       int64_t rows, const int32_t* row_order, int64_t order_len, const float* Y,
                       int64_t ldy, int f,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "wmf_als_half_step_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "wmf_als_half_step_supports": (_i32, [_i32, _i32, _i32]),
     "wmf_als_row_split_entries": (_i32, []),
+    "wmf_als_half_step_workspace_bytes_split": (_sz, [_i64, _i32, _i32, _i64]),
     "wmf_als_half_step": (_i32, [_p, _p, _p, _i64, _p, _i64, _p, _i64, _i32, _p, _i32, _p, _i64, _i32, _p, _sz, _p]),
     "wmf_sddmm_loss_workspace_bytes": (_sz, [_i64]),
     "wmf_sddmm_loss": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),

@@ -31,7 +31,7 @@ struct HalfStepParams {
 size_t simt_half_step_workspace_bytes(int f);
 int simt_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_half_step_supported(int f, int bias);
-size_t tc_half_step_workspace_bytes(int64_t rows, int f, int bias);
+size_t tc_half_step_workspace_bytes(int64_t rows, int f, int bias, int64_t segments);  // segments < 0: default scratch
 int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace wmf

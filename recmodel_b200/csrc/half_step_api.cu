@@ -22,16 +22,22 @@ int wmf_als_half_step_supports(int algo, int f, int bias) {
     return (algo == WMF_ALGO_SIMT || algo == WMF_ALGO_AUTO) ? 1 : 0;
 }
 
-size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo) {
+static size_t half_step_workspace(int64_t rows, int f, int algo, int64_t segments) {
     if (f <= 0 || f > WMF_MAX_F) return 0;
     size_t a = simt_half_step_workspace_bytes(f);
     size_t b = 0;
     if (algo != WMF_ALGO_SIMT) {
-        size_t b0 = tc_half_step_supported(f, 0) ? tc_half_step_workspace_bytes(rows, f, 0) : 0;
-        size_t b1 = tc_half_step_supported(f, 1) ? tc_half_step_workspace_bytes(rows, f, 1) : 0;
+        size_t b0 = tc_half_step_supported(f, 0) ? tc_half_step_workspace_bytes(rows, f, 0, segments) : 0;
+        size_t b1 = tc_half_step_supported(f, 1) ? tc_half_step_workspace_bytes(rows, f, 1, segments) : 0;
         b = b0 > b1 ? b0 : b1;
     }
     return a > b ? a : b;
+}
+
+size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo) { return half_step_workspace(rows, f, algo, -1); }
+
+size_t wmf_als_half_step_workspace_bytes_split(int64_t rows, int f, int algo, int64_t segments) {
+    return half_step_workspace(rows, f, algo, segments < 0 ? 0 : segments);
 }
 
 int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows,

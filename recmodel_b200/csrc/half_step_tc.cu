@@ -88,13 +88,16 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_GROUPS % 128 == 0 && GROUP_BYTES % 128 == 0 && OFF_BARS % 8 == 0 && OFF_STG % 1024 == 0, "alignment");
 
 // workspace layout (bytes): [0] SIMT row counter, [4] redo flags, [8] max diag(G), [16] total slots,
-// [20] split rows, [24] partial slots, [28] extra slots, [256, 768) profile slots, [1024, ...) split-row
-// counters, row table, partial-Gram scratch
-constexpr size_t WS_PROF = 256, WS_COUNTERS = 1024;
-constexpr int SPLIT_LEN = 8192;      // rows longer than this are cut into segments of at most this many entries
-constexpr int MAX_SPLIT_ROWS = 4096; // split rows per call (more: the rest stay whole)
-constexpr int MAX_PARTS = 2048;      // segments of split rows per call = partial-Gram scratch slots
-constexpr size_t WS_ROWTAB = WS_COUNTERS + MAX_SPLIT_ROWS * 4;
+// [20] split rows, [24] partial slots, [28] extra slots, [256, 768) profile slots, [1024, ...) row table,
+// split table, split-row counters, partial-Gram scratch
+constexpr size_t WS_PROF = 256, WS_TABLES = 1024;
+// Rows longer than this are cut into segments of at most this many entries. Two reasons: (1) balance, a row
+// never costs its CTA more than one segment; (2) accuracy: the tensor core TRUNCATES its fp32 accumulation
+// (scripts/probe/mma_round_probe.cu), a bias of ~half an ulp per MMA that grows with the number of MMAs into
+// one accumulator (measured 1.3e-4 on the solution of 8192-entry segments, 7e-6 at 1500 entries); the
+// segment partials are summed with round-to-nearest FP32 adds in segment order.
+constexpr int SPLIT_LEN = 1024;
+constexpr int DEFAULT_PARTS = 2048;  // partial slots the legacy workspace query (rows only) provides
 constexpr size_t PART_FLOATS = (size_t)F * F + F;  // a segment's S^2 W (chunk-major) and its rhs partial
 struct __align__(16) RowEnt {
     int32_t row;   // CSR row id, -1 = padding slot
@@ -283,8 +286,10 @@ __global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, in
             split_id = __shfl_sync(0xffffffffu, split_id, 0);
             first_part = __shfl_sync(0xffffffffu, first_part, 0);
             extra_base = __shfl_sync(0xffffffffu, extra_base, 0);
-            if (split_id >= MAX_SPLIT_ROWS || first_part + nseg > max_parts || extra_base + nseg - 1 > max_extra)
-                nseg = 1;  // out of scratch: this row stays whole (slow, still correct)
+            if (2 * split_id + 2 > max_parts || first_part + nseg > max_parts || extra_base + nseg - 1 > max_extra) {
+                nseg = 1;  // out of scratch: the row stays whole here and the accurate SIMT kernel redoes the half-step
+                if (lane == 0) atomicOr(reinterpret_cast<int*>(hdr_u) + 1, 4);
+            }
         }
         e.x = (int32_t)row;
         if (nseg == 1) {
@@ -338,7 +343,7 @@ template <bool PROF>
 __global__ void __launch_bounds__(THREADS, 1)
 als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const int4* __restrict__ segtab,
                         float* __restrict__ parts, int* __restrict__ counters, const uint32_t* __restrict__ hdr_u,
-                        int* __restrict__ flags) {
+                        int64_t extra_slot0, int* __restrict__ flags) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = smem_base + OFF_BARS;
@@ -381,18 +386,21 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
-    // slot k of this CTA = schedule slot k * gridDim + blockIdx
+    // This CTA walks the slots s with s % gridDim == blockIdx: first the extra slots (segments of split rows,
+    // behind the schedule in the table), then the schedule itself, so the long rows are merged early and
+    // the tail of the kernel is made of short rows.
     const int64_t total_slots = (int64_t)hdr_u[4];  // schedule + extra segment slots (set by the prep kernels)
-    const int nslots = (int)((total_slots - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const int4* mytab = rowtab + blockIdx.x;
     const int64_t tstep = gridDim.x;
+    const int nextra = (int)((total_slots - extra_slot0 - blockIdx.x + tstep - 1) / tstep);
+    const int nslots = nextra + (int)((extra_slot0 - blockIdx.x + tstep - 1) / tstep);
     auto ent_at = [&](int k) -> RowEnt {
         RowEnt e{-1, 0, 0, 0, -1};
         if (k < nslots) {
-            const int4 v = __ldg(mytab + (int64_t)k * tstep);
+            const int64_t slot = (k < nextra ? extra_slot0 + (int64_t)k * tstep : (int64_t)(k - nextra) * tstep) + blockIdx.x;
+            const int4 v = __ldg(rowtab + slot);
             e.row = v.x; e.n = v.y; e.lo = ((int64_t)(uint32_t)v.z) | ((int64_t)(v.w & 0xFFFF) << 32);
             e.sexp = (int)(((uint32_t)v.w >> 16) & 0xFFu) - 64;
-            e.part = (v.w < 0) ? k : -1;  // segment of a split row: its record sits at the same slot of the split table
+            e.part = (v.w < 0) ? (int32_t)slot : -1;  // segment of a split row: its record sits at the same slot of the split table
         }
         return e;
     };
@@ -652,7 +660,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
             if (e.part >= 0) {
                 // ---- segment of a split row: park the partial S^2 W and rhs in the scratch; the segment that arrives
                 // last adds all of them in segment order (deterministic) and goes on to solve the row
-                const int4 sg = __ldg(segtab + (int64_t)e.part * tstep + blockIdx.x);  // split_id, nseg, first_part, seg
+                const int4 sg = __ldg(segtab + e.part);  // split_id, nseg, first_part, seg
                 float* mine = parts + (size_t)(sg.z + sg.w) * PART_FLOATS;
 #pragma unroll 1
                 for (int c0 = 0; c0 < F; c0 += NB) {
@@ -868,14 +876,27 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
 
 bool tc_half_step_supported(int f, int bias) { return f == tc::F && !bias; }
 
-// header, split-row counters, row table + split table (32 bytes per slot), partial-Gram scratch for the
-// segments of split rows (f = 128 needs no SIMT slab). The public query only knows `rows`: schedules of up
-// to 2*rows + 4096 slots fit; scratch for MAX_PARTS segments (128 for matrices with fewer than 1024 rows).
-static inline size_t tc_slot_bytes(size_t slots) { return slots * 32; }
-size_t tc_half_step_workspace_bytes(int64_t rows, int f, int) {
+// Workspace: header, row table + split table (32 bytes per slot), split-row counters, partial-Gram scratch
+// for the segments of split rows (f = 128 needs no SIMT slab). Schedules of up to 2*rows + 4096 slots fit.
+struct TcLayout {
+    int64_t cap_slots, max_parts;
+    size_t off_tab, off_seg, off_cnt, off_parts, total;
+};
+static TcLayout tc_layout(int64_t sched_slots, int64_t parts) {
+    TcLayout L;
+    L.max_parts = parts < 2 ? 0 : parts;
+    L.cap_slots = sched_slots + L.max_parts;
+    L.off_tab = WS_TABLES;
+    L.off_seg = L.off_tab + 16 * (size_t)L.cap_slots;
+    L.off_cnt = L.off_seg + 16 * (size_t)L.cap_slots;
+    L.off_parts = (L.off_cnt + 4 * (size_t)(L.max_parts / 2 + 1) + 255) / 256 * 256;
+    L.total = L.off_parts + (size_t)L.max_parts * PART_FLOATS * sizeof(float);
+    return L;
+}
+size_t tc_half_step_workspace_bytes(int64_t rows, int f, int, int64_t segments) {
     const size_t a = simt_half_step_workspace_bytes(f);
-    const size_t parts = rows >= 1024 ? (size_t)MAX_PARTS : 128;
-    const size_t b = WS_ROWTAB + tc_slot_bytes((size_t)(2 * rows + 4096 + 1024) + parts) + parts * PART_FLOATS * sizeof(float);
+    if (segments < 0) segments = rows >= 1024 ? DEFAULT_PARTS : 128;
+    const size_t b = tc_layout(2 * rows + 4096 + 1024, segments + 2).total;
     return a > b ? a : b;
 }
 
@@ -886,26 +907,27 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     int grid = sms;
     if ((int64_t)grid > in.sched_len) grid = (int)in.sched_len;
     const int64_t extra_slot0 = (in.sched_len + grid - 1) / grid * grid;
-    const size_t need = WS_ROWTAB + tc_slot_bytes((size_t)extra_slot0);
+    const size_t need = tc_layout(extra_slot0, 0).total;
     if (ws == nullptr || ws_bytes < need || ws_bytes < simt_half_step_workspace_bytes(in.f)) {
         set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu (schedule of %lld slots)", ws_bytes, need,
                   (long long)in.sched_len);
         return WMF_ERR_WORKSPACE;
     }
-    // whatever is left after the tables is scratch for segments of split rows (each needs a table slot too)
-    int64_t max_parts = (int64_t)((ws_bytes - need) / (PART_FLOATS * sizeof(float) + 32));
-    if (max_parts > MAX_PARTS) max_parts = MAX_PARTS;
-    if (max_parts < 2) max_parts = 0;
-    const int64_t cap_slots = extra_slot0 + max_parts;
+    // whatever is left after the tables is scratch for the segments of split rows (each needs 34 bytes of tables too)
+    int64_t max_parts = (int64_t)((ws_bytes - need - 512) / (PART_FLOATS * sizeof(float) + 34));
+    if (ws_bytes < need + 512) max_parts = 0;
+    if (max_parts > (1ll << 24)) max_parts = 1ll << 24;
+    const TcLayout L = tc_layout(extra_slot0, max_parts);
+    max_parts = L.max_parts;
     char* base = reinterpret_cast<char*>(ws);
     int* flags = reinterpret_cast<int*>(base) + 1;  // [0] = SIMT row counter, [1] = redo flags
     float* hdr = reinterpret_cast<float*>(base);
     uint32_t* hdr_u = reinterpret_cast<uint32_t*>(base);
-    int* counters = reinterpret_cast<int*>(base + WS_COUNTERS);
-    int4* tab = reinterpret_cast<int4*>(base + WS_ROWTAB);
-    int4* segtab = tab + cap_slots;
-    float* parts = reinterpret_cast<float*>(base + WS_ROWTAB + tc_slot_bytes((size_t)cap_slots));
-    WMF_CUDA(cudaMemsetAsync(ws, 0, WS_ROWTAB + (size_t)cap_slots * 16, st));  // header, counters, empty row table
+    int4* tab = reinterpret_cast<int4*>(base + L.off_tab);
+    int4* segtab = reinterpret_cast<int4*>(base + L.off_seg);
+    int* counters = reinterpret_cast<int*>(base + L.off_cnt);
+    float* parts = reinterpret_cast<float*>(base + L.off_parts);
+    WMF_CUDA(cudaMemsetAsync(ws, 0, L.off_parts, st));  // header, empty tables, counters
     static bool attr_set = false;
     if (!attr_set) {
         WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -922,8 +944,8 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     WMF_LAUNCH_CHECK("tc_prep_rows_kernel");
     tc_finish_prep_kernel<<<1, 1, 0, st>>>(hdr_u, extra_slot0, (int)max_parts);
     WMF_LAUNCH_CHECK("tc_finish_prep_kernel");
-    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, flags);
-    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, flags);
+    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
+    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
     WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
     // fix-up: runs the FP32/LU kernel over the whole half-step only if a flag was raised
     HalfStepParams fix = in;

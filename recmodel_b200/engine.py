@@ -91,6 +91,7 @@ class DeviceCSR:
         self.shape = (int(shape[0]), int(shape[1]))
         self.nnz = int(indices.numel())
         self._row_order = None
+        self._split_segments = None
 
     @classmethod
     def from_scipy(cls, mat, device=None):
@@ -116,9 +117,21 @@ class DeviceCSR:
             self._row_order = device_schedule(self.indptr, _lib.require_device())
         return self._row_order
 
+    @property
+    def split_segments(self):
+        """Upper bound of the segments the tcgen05 half-step cuts the long rows of this matrix into
+        (include/wmf_b200.h: wmf_als_half_step_workspace_bytes_split)."""
+        if self._split_segments is None:
+            split = int(_lib.load().wmf_als_row_split_entries())
+            counts = self.indptr[1:] - self.indptr[:-1]
+            segs = torch.where(counts > split, (counts + (split - 1)) // split, torch.zeros_like(counts))
+            self._split_segments = int(segs.sum().item())
+        return self._split_segments
+
     def with_data(self, data):
         out = DeviceCSR(self.indptr, self.indices, data, self.shape)
         out._row_order = self._row_order
+        out._split_segments = self._split_segments
         return out
 
     def row_ids(self):
@@ -271,7 +284,7 @@ def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_orde
     if csr.shape[1] != Y.shape[0]:
         raise ValueError(f"count matrix has {csr.shape[1]} columns but Y has {Y.shape[0]} rows")
     X = out if out is not None else torch.empty((rows, f), dtype=torch.float32, device=Y.device)
-    need = lib.wmf_als_half_step_workspace_bytes(rows, f, algo)
+    need = lib.wmf_als_half_step_workspace_bytes_split(rows, f, algo, csr.split_segments)
     ws = workspace(need, Y.device)
     order = csr.row_order if use_row_order else None
     _lib.check(lib.wmf_als_half_step(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), rows, _ptr(order),
