@@ -349,8 +349,9 @@ def run_ours(args):
                     "ms_steps_rank0": [round(t * 1e3, 2) for t in times],
                     "what": "WMF.train(host CSR, iterations=1) incl. upload, preprocess, transpose, epoch, eval_prec, "
                             "factor read-back; 80/20 split so nnz = train nnz"},
-            # per epoch: 2 x (gram_partial, gram_reduce, tc_maxima, tc_prep_rows, als_half_step_tc, conditional SIMT fix-up)
-            "gpu_launches": 12 * args.steps,
+            # per epoch: 2 x (gram_partial, gram_reduce, tc_maxima, tc_prep_rows, tc_finish_prep, als_half_step_tc,
+            # conditional SIMT fix-up)
+            "gpu_launches": 14 * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

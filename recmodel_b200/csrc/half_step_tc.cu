@@ -94,9 +94,17 @@ constexpr size_t WS_PROF = 256, WS_TABLES = 1024;
 // Rows longer than this are cut into segments of at most this many entries. Two reasons: (1) balance, a row
 // never costs its CTA more than one segment; (2) accuracy: the tensor core TRUNCATES its fp32 accumulation
 // (scripts/probe/mma_round_probe.cu), a bias of ~half an ulp per MMA that grows with the number of MMAs into
-// one accumulator (measured 1.3e-4 on the solution of 8192-entry segments, 7e-6 at 1500 entries); the
-// segment partials are summed with round-to-nearest FP32 adds in segment order.
-constexpr int SPLIT_LEN = 1024;
+// one accumulator. Measured on the heaviest item rows at ML-20M shape (scripts/long_row_accuracy.py, error of
+// the solution against fp64; the reference's own fp32 arithmetic is 1.3e-5 there): segments of 8192 entries
+// 1.3e-4, 4096 6.2e-5, 2048 2.9e-5, 1024 1.3e-5, 512 5e-6, against 3.75 / 3.76 / 3.85 / 4.26 / 5.1 ms for the
+// item half-step (every segment parks 64 KB in L2/HBM). The segment partials are summed with
+// round-to-nearest FP32 adds in segment order. WMF_TC_SPLIT overrides the length (experiments).
+constexpr int SPLIT_LEN_DEFAULT = 2048;
+static int split_len() {
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("WMF_TC_SPLIT"); v = e ? atoi(e) : SPLIT_LEN_DEFAULT; if (v < 64) v = SPLIT_LEN_DEFAULT; v = (v + 31) / 32 * 32; }
+    return v;
+}
 constexpr int DEFAULT_PARTS = 2048;  // partial slots the legacy workspace query (rows only) provides
 constexpr size_t PART_FLOATS = (size_t)F * F + F;  // a segment's S^2 W (chunk-major) and its rhs partial
 struct __align__(16) RowEnt {
@@ -253,7 +261,7 @@ __device__ __forceinline__ int gram_scale_exp(float max_diag_g, float max_d) {
 // arithmetic never depends on the launch it is in): segment 0 stays in the row's slot, the others go to
 // extra slots behind the schedule, which the persistent CTAs reach round-robin like every other slot.
 __global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, int4* __restrict__ segtab,
-                                    uint32_t* __restrict__ hdr_u, int64_t extra_slot0, int max_extra, int max_parts) {
+                                    uint32_t* __restrict__ hdr_u, int64_t extra_slot0, int max_extra, int max_parts, int SPLIT_LEN) {
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= p.sched_len) return;
@@ -389,18 +397,19 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
     // This CTA walks the slots s with s % gridDim == blockIdx: first the extra slots (segments of split rows,
     // behind the schedule in the table), then the schedule itself, so the long rows are merged early and
     // the tail of the kernel is made of short rows.
-    const int64_t total_slots = (int64_t)hdr_u[4];  // schedule + extra segment slots (set by the prep kernels)
-    const int64_t tstep = gridDim.x;
-    const int nextra = (int)((total_slots - extra_slot0 - blockIdx.x + tstep - 1) / tstep);
-    const int nslots = nextra + (int)((extra_slot0 - blockIdx.x + tstep - 1) / tstep);
+    const int ts = (int)gridDim.x;
+    const int total_slots = (int)hdr_u[4];  // schedule + extra segment slots (set by the prep kernels), < 2^31
+    const int nextra = (total_slots - (int)extra_slot0 - (int)blockIdx.x + ts - 1) / ts;
+    const int nslots = nextra + ((int)extra_slot0 - (int)blockIdx.x + ts - 1) / ts;
+    const int base_x = (int)extra_slot0 + (int)blockIdx.x, base_s = (int)blockIdx.x - nextra * ts;
     auto ent_at = [&](int k) -> RowEnt {
         RowEnt e{-1, 0, 0, 0, -1};
         if (k < nslots) {
-            const int64_t slot = (k < nextra ? extra_slot0 + (int64_t)k * tstep : (int64_t)(k - nextra) * tstep) + blockIdx.x;
+            const int slot = k * ts + (k < nextra ? base_x : base_s);
             const int4 v = __ldg(rowtab + slot);
             e.row = v.x; e.n = v.y; e.lo = ((int64_t)(uint32_t)v.z) | ((int64_t)(v.w & 0xFFFF) << 32);
             e.sexp = (int)(((uint32_t)v.w >> 16) & 0xFFu) - 64;
-            e.part = (v.w < 0) ? (int32_t)slot : -1;  // segment of a split row: its record sits at the same slot of the split table
+            e.part = (v.w < 0) ? slot : -1;  // segment of a split row: its record sits at the same slot of the split table
         }
         return e;
     };
@@ -900,7 +909,7 @@ size_t tc_half_step_workspace_bytes(int64_t rows, int f, int, int64_t segments) 
     return a > b ? a : b;
 }
 
-int wmf_tc_split_length() { return SPLIT_LEN; }
+int wmf_tc_split_length() { return split_len(); }
 
 int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int sms = sm_count();
@@ -940,7 +949,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     tc_maxima_kernel<<<1, 32, 0, st>>>(p, hdr);
     WMF_LAUNCH_CHECK("tc_maxima_kernel");
     tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, segtab, hdr_u, extra_slot0,
-                                                                            (int)max_parts, (int)max_parts);
+                                                                            (int)max_parts, (int)max_parts, split_len());
     WMF_LAUNCH_CHECK("tc_prep_rows_kernel");
     tc_finish_prep_kernel<<<1, 1, 0, st>>>(hdr_u, extra_slot0, (int)max_parts);
     WMF_LAUNCH_CHECK("tc_finish_prep_kernel");

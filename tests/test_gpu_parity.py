@@ -262,6 +262,28 @@ def test_half_step_full_size_properties(cuda_device):
     half = users // 2
     Xa = engine.half_step(Cd.row_slice(0, half), Yd, G).cpu().numpy()
     np.testing.assert_array_equal(Xa, X[:half])
+    # (4) item side: the heaviest rows (50k-110k entries) are where an accumulation bias shows (the tensor core
+    # truncates its fp32 accumulation; long rows are cut into segments summed with round-to-nearest adds)
+    Xd = torch.from_numpy(X).to(cuda_device)
+    CTd = Cd.transpose()
+    Gi = engine.gram(Xd, 0.1)
+    Xi = engine.half_step(CTd, Xd, Gi).cpu().numpy()
+    CT = C.T.tocsr()
+    lens = np.diff(CT.indptr)
+    order = np.argsort(-lens)
+    X64 = X.astype(np.float64)
+    Gi64 = X64.T @ X64 + 0.1 * np.eye(f)
+    worst_i = 0.0
+    for r in np.concatenate([order[:3], order[200:202], order[5000:5002]]):
+        lo, hi = CT.indptr[r], CT.indptr[r + 1]
+        Yr = X64[CT.indices[lo:hi]]
+        d = CT.data[lo:hi].astype(np.float64)
+        x = np.linalg.solve(Gi64 + (Yr * d[:, None]).T @ Yr, (d + 1) @ Yr)
+        worst_i = max(worst_i, np.linalg.norm(Xi[r] - x) / np.linalg.norm(x))
+    print(f"full size, item side: worst gpu-vs-fp64 over rows of {lens[order[0]]} .. {lens[order[5001]]} entries {worst_i:.2e}")
+    assert worst_i < HALF_STEP_TOL / 2
+    Xib = engine.half_step(CTd.row_slice(0, items // 3), Xd, Gi).cpu().numpy()
+    np.testing.assert_array_equal(Xib, Xi[:items // 3])
 
 
 # ------------------------------------------------------------------------------- R8, K3
