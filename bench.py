@@ -226,8 +226,9 @@ def run_ours(args):
     engine.preprocess_(C_full.data, "log", ALPHA, BETA)
     CT_full = C_full.transpose()
     if world > 1:
-        ub = sharding.balanced_row_partition(np.diff(C_host.indptr), world, f)
-        ib = sharding.balanced_row_partition((CT_full.indptr[1:] - CT_full.indptr[:-1]).cpu().numpy(), world, f)
+        ub = sharding.balanced_row_partition(np.diff(C_host.indptr), world, f, align=engine.gram_block_rows(users))
+        ib = sharding.balanced_row_partition((CT_full.indptr[1:] - CT_full.indptr[:-1]).cpu().numpy(), world, f,
+                                             align=engine.gram_block_rows(items))
         C = C_full.row_slice(int(ub[rank]), int(ub[rank + 1]))
         CT = CT_full.row_slice(int(ib[rank]), int(ib[rank + 1]))
     else:
@@ -239,23 +240,35 @@ def run_ours(args):
     state = {"items": items_d, "users": None}
     ev_pairs = []
 
+    state["G_items"] = engine.gram(items_d, GAMMA)
+
     def epoch(record=False):
+        # row-sharded: every rank adds the Gram blocks of the shard it has just computed (one all-reduce of
+        # block partials), and the shards are all-gathered; one GPU: Gram of the full matrix
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
-        G = engine.gram(state["items"], GAMMA)
         if record:
             e[0].record()
-        X = engine.half_step(C, state["items"], G, algo=algo)
+        X = engine.half_step(C, state["items"], state["G_items"], algo=algo)
         if record:
             e[1].record()
-        state["users"] = sharding.all_gather_rows(X, ub) if world > 1 else X
-        G = engine.gram(state["users"], GAMMA)
+        if world > 1:
+            G = sharding.sharded_gram(X, ub, GAMMA)
+            state["users"] = sharding.all_gather_rows(X, ub)
+        else:
+            G = engine.gram(X, GAMMA)
+            state["users"] = X
         if record:
             e[2].record()
         Xi = engine.half_step(CT, state["users"], G, algo=algo)
         if record:
             e[3].record()
             ev_pairs.append(e)
-        state["items"] = sharding.all_gather_rows(Xi, ib) if world > 1 else Xi
+        if world > 1:
+            state["G_items"] = sharding.sharded_gram(Xi, ib, GAMMA)
+            state["items"] = sharding.all_gather_rows(Xi, ib)
+        else:
+            state["G_items"] = engine.gram(Xi, GAMMA)
+            state["items"] = Xi
 
     def sync_all():
         if world > 1:

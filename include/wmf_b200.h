@@ -60,6 +60,19 @@ int wmf_preprocess(float* data, int64_t nnz, int mode, float alpha, float beta, 
 size_t wmf_gram_workspace_bytes(int64_t n, int f);
 int wmf_gram(const float* Y, int64_t n, int f, int64_t ldy, float lambda, int ones_col0,
              float* G, void* ws, size_t ws_bytes, void* stream);
+/* The same Gram in two stages, for row-sharded runs. The n rows are cut into
+ * wmf_gram_blocks(n) blocks of wmf_gram_block_rows(n) rows (a function of n alone). wmf_gram_partials
+ * writes the double-precision partial of every block of the local slice Y[0, nloc) = global rows
+ * [row0, row0 + nloc) into `partials` (wmf_gram_workspace_bytes(n, f) bytes, block b at offset b*f*f doubles;
+ * row0 and nloc must be whole blocks, the last block of the matrix may be short). After the ranks have
+ * exchanged their blocks (blocks a rank does not own zero-filled, then one sum all-reduce: x + 0 is exact),
+ * wmf_gram_reduce adds all blocks in block order and rounds once: the same bits on every rank and the same
+ * bits wmf_gram gives on one GPU. */
+int64_t wmf_gram_block_rows(int64_t n);
+int64_t wmf_gram_blocks(int64_t n);
+int wmf_gram_partials(const float* Y, int64_t row0, int64_t nloc, int64_t n, int f, int64_t ldy, int ones_col0,
+                      void* partials, size_t partials_bytes, void* stream);
+int wmf_gram_reduce(const void* partials, int64_t n, int f, float lambda, float* G, void* stream);
 
 /* K2. One ALS half-step over `rows` CSR rows:            replaces the row loops at
  * wmf_model.py:220-239 (recompute_factors), :337-350 (recompute_factors_bias) and the Pool

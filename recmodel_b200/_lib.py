@@ -24,6 +24,10 @@ SIGNATURES = {
     "wmf_preprocess": (_i32, [_p, _i64, _i32, _f32, _f32, _p]),
     "wmf_gram_workspace_bytes": (_sz, [_i64, _i32]),
     "wmf_gram": (_i32, [_p, _i64, _i32, _i64, _f32, _i32, _p, _p, _sz, _p]),
+    "wmf_gram_block_rows": (_i64, [_i64]),
+    "wmf_gram_blocks": (_i64, [_i64]),
+    "wmf_gram_partials": (_i32, [_p, _i64, _i64, _i64, _i32, _i64, _i32, _p, _sz, _p]),
+    "wmf_gram_reduce": (_i32, [_p, _i64, _i32, _f32, _p, _p]),
     "wmf_als_half_step_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "wmf_als_half_step_supports": (_i32, [_i32, _i32, _i32]),
     "wmf_als_row_split_entries": (_i32, []),

@@ -273,6 +273,34 @@ def gram(Y, lam, ones_col0=False):
     return G
 
 
+def gram_block_rows(n):
+    """Rows per Gram block for a matrix of n rows (a function of n alone): shard boundaries of a
+    row-sharded run are multiples of it, so every rank can compute the blocks of its own rows."""
+    return int(_lib.load().wmf_gram_block_rows(int(n)))
+
+
+def gram_partials(Y_local, row0, n_total, ones_col0=False):
+    """float64 [blocks, f, f] buffer holding the Gram partials of the blocks inside the local slice
+    (global rows [row0, row0 + len(Y_local))) and zeros elsewhere; see include/wmf_b200.h."""
+    lib = _lib.load()
+    _f32(Y_local)
+    nloc, f = Y_local.shape
+    blocks = int(lib.wmf_gram_blocks(int(n_total)))
+    buf = torch.zeros((blocks, f, f), dtype=torch.float64, device=Y_local.device)
+    _lib.check(lib.wmf_gram_partials(_ptr(Y_local), int(row0), nloc, int(n_total), f, Y_local.stride(0),
+                                     int(bool(ones_col0)), _ptr(buf), buf.numel() * 8, _stream()), "wmf_gram_partials")
+    return buf
+
+
+def gram_from_partials(partials, n_total, lam):
+    """G from the (exchanged) block partials: blocks added in block order, rounded once, + lam I."""
+    lib = _lib.load()
+    f = partials.shape[1]
+    G = torch.empty((f, f), dtype=torch.float32, device=partials.device)
+    _lib.check(lib.wmf_gram_reduce(_ptr(partials), int(n_total), f, float(lam), _ptr(G), _stream()), "wmf_gram_reduce")
+    return G
+
+
 def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_order=True):
     """X = one ALS half-step over the rows of ``csr`` against fixed factors Y
     (wmf_model.py:213-240 / :311-351)."""

@@ -24,9 +24,10 @@ def row_costs(counts, f):
     return counts * float(f) * f + np.where(counts > 0, float(f) ** 3 / 3.0, 1.0)
 
 
-def balanced_row_partition(counts, world, f):
+def balanced_row_partition(counts, world, f, align=1):
     """Contiguous row ranges [b[g], b[g+1]) with near-equal summed cost. Returns int64 array of
-    world+1 boundaries (monotone, b[0]=0, b[-1]=rows)."""
+    world+1 boundaries (monotone, b[0]=0, b[-1]=rows). Inner boundaries are rounded to multiples of
+    ``align`` (the Gram block height, so that every rank owns whole Gram blocks)."""
     counts = np.asarray(counts)
     rows = len(counts)
     if world <= 1 or rows == 0:
@@ -34,8 +35,23 @@ def balanced_row_partition(counts, world, f):
     csum = np.cumsum(row_costs(counts, f))
     targets = csum[-1] * np.arange(1, world) / world
     cuts = np.searchsorted(csum, targets, side="left") + 1
+    if align > 1:
+        cuts = (cuts + align // 2) // align * align
     bounds = np.concatenate([[0], np.minimum(cuts, rows), [rows]]).astype(np.int64)
     return np.maximum.accumulate(bounds)
+
+
+def sharded_gram(X_local, bounds, lam, ones_col0=False, group=None):
+    """G = X^T X + lam I of the full factor matrix from this rank's freshly computed shard: block partials
+    of the local rows, one sum all-reduce (foreign blocks are zeros, so the sum is exact), blocks added in
+    block order. Same bits as the single-GPU Gram of the gathered matrix."""
+    from . import engine
+    rank, world = dist_info(group)
+    n_total = int(bounds[-1])
+    partials = engine.gram_partials(X_local, int(bounds[rank]), n_total, ones_col0=ones_col0)
+    if world > 1:
+        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+    return engine.gram_from_partials(partials, n_total, lam)
 
 
 def all_gather_rows(local, bounds, group=None):

@@ -244,8 +244,8 @@ class WMF(RecModel):
         if distributed:
             ucounts = (C_full.indptr[1:] - C_full.indptr[:-1]).cpu().numpy()
             icounts = (CT_full.indptr[1:] - CT_full.indptr[:-1]).cpu().numpy()
-            ub = sharding.balanced_row_partition(ucounts, world, f)
-            ib = sharding.balanced_row_partition(icounts, world, f)
+            ub = sharding.balanced_row_partition(ucounts, world, f, align=engine.gram_block_rows(len(ucounts)))
+            ib = sharding.balanced_row_partition(icounts, world, f, align=engine.gram_block_rows(len(icounts)))
             C = C_full.row_slice(int(ub[rank_id]), int(ub[rank_id + 1]))
             CT = CT_full.row_slice(int(ib[rank_id]), int(ib[rank_id + 1]))
             eval_d = self._eval_csr(eval_mat, ub, rank_id)
@@ -259,6 +259,7 @@ class WMF(RecModel):
         last_mse, count_improvement = -np.inf, 0
         it = None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        G_items = None
         for it in range(iterations):
             if verbose > 0:
                 print(f"Starting fitting iteration {it}")
@@ -269,14 +270,26 @@ class WMF(RecModel):
             start = time.time()
             ev[0].record()
             # users from items (:143 / :151), then items from users (:144 / :152)
-            G = engine.gram(self.items_device, self.gamma, ones_col0=bias)
-            X = engine.half_step(C, self.items_device, G, bias=bias, algo=algo)
-            users = sharding.all_gather_rows(X, ub) if distributed else X
+            # Gram of the fixed side: on one GPU from the full matrix; row-sharded, every rank contributes the
+            # blocks of the shard it has just computed (same bits, see sharding.sharded_gram)
+            if G_items is None:
+                G_items = engine.gram(self.items_device, self.gamma, ones_col0=bias)
+            X = engine.half_step(C, self.items_device, G_items, bias=bias, algo=algo)
+            if distributed:
+                G = sharding.sharded_gram(X, ub, self.gamma, ones_col0=bias)
+                users = sharding.all_gather_rows(X, ub)
+            else:
+                G = engine.gram(X, self.gamma, ones_col0=bias)
+                users = X
             self._set_device_factors(users=users)
             ev[1].record()
-            G = engine.gram(users, self.gamma, ones_col0=bias)
             Xi = engine.half_step(CT, users, G, bias=bias, algo=algo)
-            items = sharding.all_gather_rows(Xi, ib) if distributed else Xi
+            if distributed:
+                G_items = sharding.sharded_gram(Xi, ib, self.gamma, ones_col0=bias)
+                items = sharding.all_gather_rows(Xi, ib)
+            else:
+                G_items = None
+                items = Xi
             self._set_device_factors(items=items)
             ev[2].record()
             if eval_d is None:

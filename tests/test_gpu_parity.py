@@ -76,6 +76,28 @@ def test_gram_matches_fp64(cuda_device, n, f, ones):
     np.testing.assert_array_equal(G, G2)  # deterministic reduction order
 
 
+@pytest.mark.parametrize("n,f,ones", [(26_744, 128, False), (3706, 65, True), (700, 16, False), (31, 8, False)])
+def test_gram_block_partials_reproduce_gram(cuda_device, n, f, ones):
+    """Row-sharded Gram: block partials computed shard by shard (foreign blocks zero) and summed reproduce
+    the one-call Gram bit for bit, for any split into whole blocks (include/wmf_b200.h)."""
+    from recmodel_b200 import sharding
+    Y = (np.random.default_rng(n).standard_normal((n, f)) * 0.5 + 0.3).astype(np.float32)
+    Yd = dev(Y, cuda_device)
+    G = engine.gram(Yd, 0.1, ones_col0=ones).cpu().numpy()
+    B = engine.gram_block_rows(n)
+    counts = np.random.default_rng(1).integers(0, 50, n)
+    for world in (2, 3, 8):
+        bounds = sharding.balanced_row_partition(counts, world, f, align=B)
+        assert all(b % B == 0 or b == n for b in bounds)
+        total = None
+        for g in range(world):
+            part = engine.gram_partials(Yd[int(bounds[g]):int(bounds[g + 1])], int(bounds[g]), n, ones_col0=ones)
+            total = part if total is None else total + part  # what the sum all-reduce does (x + 0 is exact)
+        G2 = engine.gram_from_partials(total, n, 0.1).cpu().numpy()
+        np.testing.assert_array_equal(G, G2)
+    np.testing.assert_array_equal(G, G.T)
+
+
 def test_transpose_matches_scipy(cuda_device):
     C = make_counts(700, 450, 20_000, seed=21)
     CT = DeviceCSR.from_scipy(C, cuda_device).transpose().to_scipy()

@@ -55,6 +55,12 @@ def test_balanced_row_partition_properties():
         per = np.array([cost[b[g]:b[g + 1]].sum() for g in range(world)])
         assert per.max() <= cost.sum() / world + cost.max() + 1e-6
     assert list(sharding.balanced_row_partition(np.zeros(0), 4, 16)) == [0, 0, 0, 0, 0]
+    # aligned to the Gram block height (sharding.sharded_gram): inner boundaries are whole blocks
+    for world in (2, 3, 8):
+        b = sharding.balanced_row_partition(counts, world, 128, align=32)
+        assert b[0] == 0 and b[-1] == len(counts) and np.all(np.diff(b) >= 0) and np.all(b[:-1] % 32 == 0)
+        per = np.array([cost[b[g]:b[g + 1]].sum() for g in range(world)])
+        assert per.max() <= cost.sum() / world + 2 * cost.max() + np.sort(cost)[-32:].sum()
 
 
 WORKER = r"""
@@ -78,6 +84,24 @@ Il = orc.half_step(users, CT[ib[rank]:ib[rank+1]], 0.1)
 items = sharding.all_gather_rows(torch.from_numpy(Il), ib).numpy()
 ref_u = orc.half_step(Y, C, 0.1); ref_i = orc.half_step(ref_u, CT, 0.1)
 assert np.array_equal(users, ref_u) and np.array_equal(items, ref_i), "sharded != single"
+# Gram of the new factors from block partials: each rank fills the blocks of its own rows (NumPy stands in
+# for wmf_gram_partials), zeros elsewhere, one sum all-reduce, blocks added in block order
+from recmodel_b200 import engine
+B = engine.gram_block_rows(90)
+ub2 = sharding.balanced_row_partition(np.diff(C.indptr), world, 8, align=B)
+assert all(int(b) % B == 0 for b in ub2[:-1])
+nb = -(-90 // B)
+def block(b, X):
+    Xb = X[b * B:(b + 1) * B].astype(np.float64)
+    return Xb.T @ Xb
+part = torch.zeros((nb, 8, 8), dtype=torch.float64)
+for b in range(int(ub2[rank]) // B, -(-int(ub2[rank + 1]) // B)):
+    part[b] = torch.from_numpy(block(b, ref_u))
+sharding.all_reduce_sum_(part)
+single = np.zeros((8, 8)); summed = np.zeros((8, 8))
+for b in range(nb):
+    single = single + block(b, ref_u); summed = summed + part[b].numpy()
+assert np.array_equal(single, summed), "block partial exchange changed the Gram"
 s = torch.tensor([1.0 + rank, 2.0, 3.0], dtype=torch.float64)
 sharding.all_reduce_sum_(s)
 assert s.tolist() == [3.0, 4.0, 6.0]
