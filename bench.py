@@ -237,38 +237,17 @@ def run_ours(args):
     C.row_order, CT.row_order  # noqa: B018
     del C_full, CT_full
     items_d = torch.from_numpy(orc.init_items(items, dim, False)).to(device)
-    state = {"items": items_d, "users": None}
+    from recmodel_b200.epoch import ResidentEpoch
+    # the epoch as four replayable CUDA graphs (half-step | exchange | half-step | exchange); --no-graphs
+    # launches the same sequence from Python
+    loop = ResidentEpoch(C, CT, items_d, GAMMA, bias=False, algo=algo, ub=ub, ib=ib, graphs=not args.no_graphs)
     ev_pairs = []
 
-    state["G_items"] = engine.gram(items_d, GAMMA)
-
     def epoch(record=False):
-        # row-sharded: every rank adds the Gram blocks of the shard it has just computed (one all-reduce of
-        # block partials), and the shards are all-gathered; one GPU: Gram of the full matrix
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        loop.step(e)
         if record:
-            e[0].record()
-        X = engine.half_step(C, state["items"], state["G_items"], algo=algo)
-        if record:
-            e[1].record()
-        if world > 1:
-            G = sharding.sharded_gram(X, ub, GAMMA)
-            state["users"] = sharding.all_gather_rows(X, ub)
-        else:
-            G = engine.gram(X, GAMMA)
-            state["users"] = X
-        if record:
-            e[2].record()
-        Xi = engine.half_step(CT, state["users"], G, algo=algo)
-        if record:
-            e[3].record()
             ev_pairs.append(e)
-        if world > 1:
-            state["G_items"] = sharding.sharded_gram(Xi, ib, GAMMA)
-            state["items"] = sharding.all_gather_rows(Xi, ib)
-        else:
-            state["G_items"] = engine.gram(Xi, GAMMA)
-            state["items"] = Xi
 
     def sync_all():
         if world > 1:
@@ -348,7 +327,8 @@ def run_ours(args):
                                     "log preprocessing (BASELINE.json configs[1])") if args.workload == "ml20m"
                        else args.workload,
                        "l2": "inputs larger than L2 (2 x 160 MB CSR + 85 MB factors streamed per epoch)",
-                       "algo": args.algo, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU"},
+                       "algo": args.algo, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                       "launch": "python" if args.no_graphs else "4 CUDA graphs per epoch"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic() if world == 1 else None,
                          "traffic_note": "DRAM read+write bytes of the same two launches (ncu --set full, profiles/); "
@@ -369,7 +349,16 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured NCCL collectives keep the communicator busy at teardown (destroy_process_group was seen to
+        # hang with live graphs): drop the graphs, drain the device, meet once more and leave without it.
+        loop.graphs = None
+        del loop
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        torch.cuda.synchronize(device)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -382,6 +371,7 @@ def main():
     ap.add_argument("--algo", choices=["auto", "simt", "tcgen05"], default="auto")
     ap.add_argument("--cpu-frac", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the epoch from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

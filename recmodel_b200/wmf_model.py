@@ -170,11 +170,19 @@ class WMF(RecModel):
                 raise AttributeError("'NoneType' object has no attribute 'data' (weighted training needs count_mat)")
             if pre_process_count not in ("log", "linear"):
                 raise ValueError(f"Pre_process_count {pre_process_count} is not implement please use log or linear.")
-            C_full = DeviceCSR.from_scipy(count_mat, dev)
+            ub = None
+            if world > 1:  # every rank uploads its own rows only; the slices are all-gathered over NVLink
+                count_mat = count_mat.tocsr()
+                f_cost = self.dim + (1 if self.bias is True else 0)
+                ub = sharding.balanced_row_partition(np.diff(count_mat.indptr), world, f_cost,
+                                                     align=engine.gram_block_rows(count_mat.shape[0]))
+                C_full = DeviceCSR.from_scipy_sharded(count_mat, dev, ub)
+            else:
+                C_full = DeviceCSR.from_scipy(count_mat, dev)
             C_full = C_full.with_data(engine.preprocess_(C_full.data, pre_process_count, alpha, beta))
             CT_full = C_full.transpose()  # count_mat.T.tocsr()  (:128)
             it = self._train_weighted(C_full, CT_full, util_d, iterations, verbose, eval_mat, cores, stopping_rounds,
-                                      min_improvement, stats, rank_id, world)
+                                      min_improvement, stats, rank_id, world, ub)
         torch.cuda.synchronize(dev)
         stats["total_ms"] = (time.perf_counter() - t_start) * 1e3
         self.last_train_stats = stats
@@ -236,15 +244,16 @@ class WMF(RecModel):
         return it
 
     def _train_weighted(self, C_full, CT_full, util_d, iterations, verbose, eval_mat, cores, stopping_rounds,
-                        min_improvement, stats, rank_id, world):
+                        min_improvement, stats, rank_id, world, ub=None):
         bias = self.bias is True
         algo = _ALGOS[self.algo]
         f = self.items.shape[1] if self.items is not None else self.dim
         distributed = world > 1
         if distributed:
-            ucounts = (C_full.indptr[1:] - C_full.indptr[:-1]).cpu().numpy()
             icounts = (CT_full.indptr[1:] - CT_full.indptr[:-1]).cpu().numpy()
-            ub = sharding.balanced_row_partition(ucounts, world, f, align=engine.gram_block_rows(len(ucounts)))
+            if ub is None:
+                ucounts = (C_full.indptr[1:] - C_full.indptr[:-1]).cpu().numpy()
+                ub = sharding.balanced_row_partition(ucounts, world, f, align=engine.gram_block_rows(len(ucounts)))
             ib = sharding.balanced_row_partition(icounts, world, f, align=engine.gram_block_rows(len(icounts)))
             C = C_full.row_slice(int(ub[rank_id]), int(ub[rank_id + 1]))
             CT = CT_full.row_slice(int(ib[rank_id]), int(ib[rank_id + 1]))
