@@ -48,7 +48,7 @@ class ResidentEpoch:
     def _user_exchange(self):
         if self.world > 1:
             self.G_users.copy_(sharding.sharded_gram(self.X_users, self.ub, self.gamma, ones_col0=self.bias))
-            self.users.copy_(sharding.all_gather_rows(self.X_users, self.ub))
+            sharding.all_gather_rows(self.X_users, self.ub, out=self.users)
         else:
             self.G_users.copy_(engine.gram(self.users, self.gamma, ones_col0=self.bias))
 
@@ -58,7 +58,7 @@ class ResidentEpoch:
     def _item_exchange(self):
         if self.world > 1:
             self.G_items.copy_(sharding.sharded_gram(self.X_items, self.ib, self.gamma, ones_col0=self.bias))
-            self.items.copy_(sharding.all_gather_rows(self.X_items, self.ib))
+            sharding.all_gather_rows(self.X_items, self.ib, out=self.items)
         else:
             self.G_items.copy_(engine.gram(self.items, self.gamma, ones_col0=self.bias))
 

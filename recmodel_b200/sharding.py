@@ -54,27 +54,33 @@ def sharded_gram(X_local, bounds, lam, ones_col0=False, group=None):
     return engine.gram_from_partials(partials, n_total, lam)
 
 
-def all_gather_rows(local, bounds, group=None):
-    """Concatenate row shards [bounds[g], bounds[g+1]) from every rank into the full matrix.
-    Shards have different heights, so each rank pads to the tallest shard; one all-gather."""
+def all_gather_rows(local, bounds, group=None, out=None):
+    """Concatenate row shards [bounds[g], bounds[g+1]) from every rank into the full matrix. Shards have
+    different heights: the gather writes every shard straight into its rows of ``out`` (allocated if None), no
+    padding and no repacking copies."""
     rank, world = dist_info(group)
     if world == 1:
-        return local
-    heights = np.diff(bounds)
-    hmax = int(heights.max())
+        if out is None:
+            return local
+        out.copy_(local)
+        return out
     f = local.shape[1]
-    send = local
-    if local.shape[0] != hmax:
-        send = torch.zeros((hmax, f), dtype=local.dtype, device=local.device)
-        send[: local.shape[0]] = local
+    if out is None:
+        out = torch.empty((int(bounds[-1]), f), dtype=local.dtype, device=local.device)
+    heights = np.diff(bounds)
+    if dist.get_backend(group) == "nccl" or int(heights.min()) == int(heights.max()):
+        views = [out[int(bounds[g]):int(bounds[g + 1])] for g in range(world)]
+        dist.all_gather(views, local.contiguous(), group=group)
+        return out
+    # backends without uneven all-gather (gloo, in the CPU tests): pad to the tallest shard, gather, unpack
+    hmax = int(heights.max())
+    send = torch.zeros((hmax, f), dtype=local.dtype, device=local.device)
+    send[: local.shape[0]] = local
     recv = torch.empty((world * hmax, f), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
-    if int(heights.min()) == hmax:
-        return recv
-    full = torch.empty((int(bounds[-1]), f), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
     for g in range(world):
-        full[int(bounds[g]):int(bounds[g + 1])] = recv[g * hmax: g * hmax + int(heights[g])]
-    return full
+        out[int(bounds[g]):int(bounds[g + 1])] = recv[g * hmax: g * hmax + int(heights[g])]
+    return out
 
 
 def all_reduce_sum_(t, group=None):
