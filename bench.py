@@ -44,8 +44,8 @@ def env_int(name, default):
 
 def load_traffic():
     """DRAM bytes (read + write) of the two half-step launches of one epoch from the committed
-    `ncu --set full` capture (profiles/r01_ncu_traffic.json); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    `ncu --set full` capture (profiles/r01c_ncu_traffic.json); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01c_ncu_traffic.json")
     try:
         with open(path) as fh:
             t = json.load(fh)
