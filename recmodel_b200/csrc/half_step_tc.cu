@@ -529,17 +529,29 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
             const uint32_t tile_h = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + m * 128;
             const int half = s & 1;
             float part = 0.f;
-#pragma unroll
-            for (int c = 0; c < SUB / 8; ++c) {   // one 16-byte chunk = 8 entries of this feature
+            // The shared-memory accessors are volatile asm (program order is issue order), so the loads of chunk c+1
+            // are written ahead of the arithmetic and stores of chunk c: one LDS latency is exposed per sub-chunk
+            // instead of one per 8 entries.
+            float vn[8], sqn[8], dpn[8];
+            auto load_chunk = [&](int c) {
                 const float4 sa = lds4(mt + c * 32), sb4 = lds4(mt + c * 32 + 16);
                 const float4 da = lds4(mt + SUB * 4 + c * 32), db = lds4(mt + SUB * 4 + c * 32 + 16);
-                const float sq[8] = {sa.x, sa.y, sa.z, sa.w, sb4.x, sb4.y, sb4.z, sb4.w};
-                const float dp[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                sqn[0] = sa.x; sqn[1] = sa.y; sqn[2] = sa.z; sqn[3] = sa.w; sqn[4] = sb4.x; sqn[5] = sb4.y; sqn[6] = sb4.z; sqn[7] = sb4.w;
+                dpn[0] = da.x; dpn[1] = da.y; dpn[2] = da.z; dpn[3] = da.w; dpn[4] = db.x; dpn[5] = db.y; dpn[6] = db.z; dpn[7] = db.w;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) vn[e] = lds1(stg + (c * 8 + e) * 128);
+            };
+            load_chunk(0);
+#pragma unroll
+            for (int c = 0; c < SUB / 8; ++c) {   // one 16-byte chunk = 8 entries of this feature
+                float v[8], sq[8], dp[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { v[e] = vn[e]; sq[e] = sqn[e]; dp[e] = dpn[e]; }
+                if (c + 1 < SUB / 8) load_chunk(c + 1);
                 uint32_t hh[4], ll[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float v0 = lds1(stg + (c * 8 + 2 * e) * 128);
-                    const float v1 = lds1(stg + (c * 8 + 2 * e + 1) * 128);
+                    const float v0 = v[2 * e], v1 = v[2 * e + 1];
                     const float z0 = sq[2 * e] * v0, z1 = sq[2 * e + 1] * v1;
                     part = fmaf(dp[2 * e], v0, part);
                     part = fmaf(dp[2 * e + 1], v1, part);
