@@ -120,6 +120,17 @@ int wmf_predict_pairs(const int64_t* users, int64_t user_stride, const int64_t* 
                       const float* U, int64_t ldu, const float* V, int64_t ldv, int f, int bias,
                       float* out, void* stream);
 
+/* N2. Counting step of the sampled Recall@N protocol:    replaces the rank + `item in top[:k]` loop of
+ * RecModel.compute_hit (base_model.py:84-95) for every held-out interaction at once.
+ * S [nu x L] are the bit-exact scores (wmf_predict_pairs) of each user's drawn candidate list cand [nu x L]
+ * (int32 item ids), slot[u] the position the held-out item overwrites (base_model.py:79-80). For interaction p
+ * = (pair_user[p] = row of S/cand, pair_item[p], pair_score[p] = its exact score) ahead[p] receives the number
+ * of candidates WMF.rank puts ahead of the item (higher score, or equal score at a lower position; a second
+ * copy of the item id in the list counts as the item). The item is in top[:k] iff ahead[p] < k. */
+int wmf_rank_ahead(const float* S, const int32_t* cand, const int32_t* slot, int64_t nu, int64_t L,
+                   const int32_t* pair_user, const int32_t* pair_item, const float* pair_score, int64_t np,
+                   int32_t* ahead, void* stream);
+
 /* K4+K5. Top-N over a candidate list for a batch of users: replaces WMF.rank (:25-47).
  * Scores are the bit-exact fp32 scores of wmf_predict_pairs, so the selected index SET equals
  * the reference's; order is descending score, ties broken by lower candidate position.

@@ -30,6 +30,7 @@ SIGNATURES = {
     "wmf_gram_reduce": (_i32, [_p, _i64, _i32, _f32, _p, _p]),
     "wmf_als_half_step_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "wmf_als_half_step_supports": (_i32, [_i32, _i32, _i32]),
+    "wmf_rank_ahead": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _p, _p]),
     "wmf_als_row_split_entries": (_i32, []),
     "wmf_als_half_step_workspace_bytes_split": (_sz, [_i64, _i32, _i32, _i64]),
     "wmf_als_half_step": (_i32, [_p, _p, _p, _i64, _p, _i64, _p, _i64, _i32, _p, _i32, _p, _i64, _i32, _p, _sz, _p]),

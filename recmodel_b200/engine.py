@@ -386,6 +386,21 @@ def predict_pairs(users, items, U, V, bias=False):
     return out
 
 
+def rank_ahead(S, cand, slot, pair_user, pair_item, pair_score):
+    """int32 [pairs]: how many candidates of its user's list WMF.rank puts ahead of each held-out item
+    (include/wmf_b200.h: wmf_rank_ahead; base_model.py:84-95)."""
+    lib = _lib.load()
+    _f32(S)
+    nu, L = S.shape
+    n = pair_user.numel()
+    out = torch.empty(n, dtype=torch.int32, device=S.device)
+    assert cand.dtype == torch.int32 and slot.dtype == torch.int32 and pair_user.dtype == torch.int32
+    assert pair_item.dtype == torch.int32 and pair_score.dtype == torch.float32 and cand.shape == S.shape
+    _lib.check(lib.wmf_rank_ahead(_ptr(S), _ptr(cand), _ptr(slot), nu, L, _ptr(pair_user), _ptr(pair_item),
+                                  _ptr(pair_score), n, _ptr(out), _stream()), "wmf_rank_ahead")
+    return out
+
+
 def score_topk(users, cand, U, V, topn, bias=False, want_scores=False):
     """Top-``topn`` candidate ids [nu x topn] (int64), best first, for each user in ``users``
     over the shared candidate list ``cand`` (None = all items) (wmf_model.py:25-47)."""

@@ -347,6 +347,55 @@ class WMF(RecModel):
         mse = s[0] / s[2]
         return np.float32(np.sqrt(mse)) if metric == "RMSE" else np.float32(mse)
 
+    # ---------------------------------------------------------------- eval_topn (R12)
+    def eval_topn(self, test_mat, train_mat=None, eval_mat=None, topn=[10], rand_sampled=1000, cores=1,
+                  random_state=None, dtype="float32"):
+        """Sampled Recall@N with the reference's protocol and RNG draw order (base_model.py:51-148), all
+        held-out interactions ranked in one device pass instead of one ``rank`` call each: per user the
+        candidate list and the slot are drawn on the host exactly as ``compute_hit`` does (:79-80), the
+        list is scored once (bit-exact ``predict`` scores), and ``item in top[:k]`` becomes "fewer than k
+        candidates are ranked ahead of it" (``wmf_rank_ahead``; ties by position like ``rank``).
+        ``RecModel.eval_topn(self, ...)`` is the per-interaction host loop with the same results."""
+        for other in (train_mat, eval_mat):
+            if other is not None and other.shape != test_mat.shape:
+                raise ValueError("inconsistent shapes")  # what `test_mat + other` raises (:115-120)
+        if random_state is not None:
+            np.random.seed(random_state)
+        if not isinstance(topn, np.ndarray):
+            raise ValueError("Topn has to be a np.array")
+        test_mat = test_mat.tocsr()
+        indptr = np.asarray(test_mat.indptr, dtype=np.int64)
+        counts = np.diff(indptr)
+        with_test = np.flatnonzero(counts > 0)
+        L = int(rand_sampled) + 1
+        kmax = int(topn.max())
+        cand = np.empty((len(with_test), L), dtype=np.int32)
+        slot = np.empty(len(with_test), dtype=np.int32)
+        for k in range(len(with_test)):  # the reference's draw order: users in row order, list then slot
+            cand[k] = np.random.randint(0, self.num_items, size=(rand_sampled + 1))
+            slot[k] = np.random.randint(0, rand_sampled - (2 * kmax))
+        hits = np.zeros(topn.shape, dtype=np.int64)
+        dev = self.device
+        U, V, bias = self.users_device, self.items_device, self.bias is True
+        topn_d = torch.from_numpy(np.ascontiguousarray(topn, dtype=np.int32)).to(dev)
+        step = max(1, (1 << 25) // L)  # users per pass: at most 32 M list scores resident
+        for k0 in range(0, len(with_test), step):
+            k1 = min(k0 + step, len(with_test))
+            users = torch.from_numpy(with_test[k0:k1]).to(dev)
+            cand_d = torch.from_numpy(cand[k0:k1]).to(dev)
+            slot_d = torch.from_numpy(slot[k0:k1]).to(dev)
+            S = engine.predict_pairs(users.repeat_interleave(L), cand_d.reshape(-1).to(torch.int64), U, V,
+                                     bias=bias).reshape(k1 - k0, L)
+            lo, hi = int(indptr[with_test[k0]]), int(indptr[with_test[k1 - 1] + 1])
+            n_per = torch.from_numpy(counts[with_test[k0:k1]]).to(dev)
+            pair_user = torch.arange(k1 - k0, device=dev, dtype=torch.int32).repeat_interleave(n_per)
+            pair_item = torch.from_numpy(np.ascontiguousarray(test_mat.indices[lo:hi], dtype=np.int32)).to(dev)
+            pair_score = engine.predict_pairs(users[pair_user.long()], pair_item.to(torch.int64), U, V, bias=bias)
+            ahead = engine.rank_ahead(S, cand_d, slot_d, pair_user, pair_item, pair_score)
+            hits += (ahead[:, None] < topn_d[None, :]).sum(0).cpu().numpy()
+        recall = hits.astype(dtype) / len(test_mat.nonzero()[0])
+        return {f"Recall@{topn[pos]}": recall[pos] for pos in range(len(topn))}
+
     # ---------------------------------------------------------------- predict (R8)
     def predict(self, users, items):
         """Scores f(user_k, item_k); one user against many items broadcasts (wmf_model.py:191-211).

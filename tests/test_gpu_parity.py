@@ -528,6 +528,34 @@ def test_unweighted_vs_golden(cuda_device):
     assert float(m.eval_prec(te)) == pytest.approx(float(g["mse_final"]), rel=2e-3)
 
 
+@pytest.mark.parametrize("dim,bias,items,rs", [(16, False, 800, 200), (12, True, 90, 60), (128, False, 3000, 1000)])
+def test_eval_topn_device_equals_host_loop(cuda_device, dim, bias, items, rs):
+    """the batched device protocol (one scoring pass + wmf_rank_ahead) returns exactly what the
+    reference's loop of rank calls returns (base_model.py:51-148), same RNG draws. The small-catalogue case draws
+    lists with many repeated ids (90 items, 61 draws), which exercises the `item in top` duplicate rule."""
+    from recmodel_b200.base_model import RecModel
+    users = 400
+    full = make_counts(users, items, min(users * items // 8, 30_000), seed=5, planted_rank=4)
+    tr, te = split_train_test(full)
+    m = WMF(num_items=items, num_users=users, dim=dim, gamma=0.1, weighted=True, bias=bias)
+    m.train(tr, 2, eval_mat=te, count_mat=tr, cores=1, stopping_rounds=99)
+    topn = np.array([1, 5, 20])
+    dev_res = m.eval_topn(te.copy(), topn=topn, rand_sampled=rs, random_state=11)
+    host_res = RecModel.eval_topn(m, te.copy(), topn=topn, rand_sampled=rs, random_state=11)
+    assert dev_res.keys() == host_res.keys()
+    for k in dev_res:
+        assert float(dev_res[k]) == float(host_res[k]), (k, dev_res[k], host_res[k])
+    # exact score ties: all-equal factors make every score equal, so only positions decide
+    m.users = np.ones_like(m.users)
+    m.items = np.ones_like(m.items)
+    dev_res = m.eval_topn(te.copy(), topn=topn, rand_sampled=rs, random_state=12)
+    host_res = RecModel.eval_topn(m, te.copy(), topn=topn, rand_sampled=rs, random_state=12)
+    for k in dev_res:
+        assert float(dev_res[k]) == float(host_res[k]), (k, dev_res[k], host_res[k])
+    with pytest.raises(ValueError):
+        m.eval_topn(te, topn=[10])
+
+
 def test_recall_quality_planted_structure(cuda_device):
     """End-to-end quality: Recall@20 on a planted low-rank matrix vs the oracle trained the same
     way (north_star: within 0.005 absolute)."""
