@@ -556,6 +556,27 @@ def test_eval_topn_device_equals_host_loop(cuda_device, dim, bias, items, rs):
         m.eval_topn(te, topn=[10])
 
 
+def test_coverage_and_split_mirror_reference_utils(cuda_device):
+    """utils.test_coverage batched on the device equals the reference's per-user loop, and
+    train_test_split_sparse_mat keeps the reference's RNG semantics (utils.py:3-37)."""
+    from recmodel_b200 import utils
+    full = make_counts(700, 300, 20_000, seed=8, planted_rank=5)  # users >= items: the reference sizes the counts by users
+    tr, te = utils.train_test_split_sparse_mat(full, train=0.8, seed=1993)
+    np.random.seed(1993)
+    mask = np.random.rand(full.nnz) < 0.8
+    assert tr.nnz == int(mask.sum()) and te.nnz == full.nnz - tr.nnz and (tr + te != full).nnz == 0
+    m = WMF(num_items=300, num_users=700, dim=16, gamma=0.1, weighted=True)
+    m.train(tr, 2, eval_mat=te, count_mat=tr, cores=1, stopping_rounds=99)
+    got = utils.test_coverage(m, tr, 10)
+
+    class LoopOnly:  # no rank_batch: forces the reference's per-user loop through the same device rank
+        def rank(self, items, users, topn=None):
+            return m.rank(items, users, topn)
+    ref = utils.test_coverage(LoopOnly(), tr, 10)
+    np.testing.assert_array_equal(got, ref)
+    assert got.shape == (700,) and got.sum() == 700 * 10
+
+
 def test_recall_quality_planted_structure(cuda_device):
     """End-to-end quality: Recall@20 on a planted low-rank matrix vs the oracle trained the same
     way (north_star: within 0.005 absolute)."""
