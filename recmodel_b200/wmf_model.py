@@ -79,7 +79,13 @@ class WMF(RecModel):
     @property
     def users(self):
         if self._users_h is None and self._users_d is not None:
-            self._users_h = engine.d2h(self._users_d)
+            pre = getattr(self, "_users_prefetch", None)
+            if pre is not None and pre[0] is self._users_d:  # read back while the item half-step was running
+                pre[2].synchronize()
+                self._users_h = pre[1].numpy()
+            else:
+                self._users_h = engine.d2h(self._users_d)
+            self._users_prefetch = None
         return self._users_h
 
     @users.setter
@@ -269,6 +275,11 @@ class WMF(RecModel):
         it = None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         G_items = None
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self.device)
+        eval_ready = None
+        self._users_prefetch = None
         for it in range(iterations):
             if verbose > 0:
                 print(f"Starting fitting iteration {it}")
@@ -284,6 +295,13 @@ class WMF(RecModel):
             if G_items is None:
                 G_items = engine.gram(self.items_device, self.gamma, ones_col0=bias)
             X = engine.half_step(C, self.items_device, G_items, bias=bias, algo=algo)
+            if eval_d is None and eval_mat is not None:
+                # the evaluation matrix goes up on a side stream while the half-step runs (a missing one still
+                # fails below, where the reference fails, :163)
+                with torch.cuda.stream(side):
+                    eval_d = self._eval_csr(eval_mat)
+                    eval_ready = torch.cuda.Event()
+                    eval_ready.record(side)
             if distributed:
                 G = sharding.sharded_gram(X, ub, self.gamma, ones_col0=bias)
                 users = sharding.all_gather_rows(X, ub)
@@ -292,6 +310,16 @@ class WMF(RecModel):
                 users = X
             self._set_device_factors(users=users)
             ev[1].record()
+            if it == iterations - 1:
+                # last epoch: the user factors are final, read them back while the item half-step runs
+                side.wait_event(ev[1])
+                with torch.cuda.stream(side):
+                    host = torch.empty(users.shape, dtype=users.dtype, pin_memory=True)
+                    host.copy_(users, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                users.record_stream(side)
+                self._users_prefetch = (users, host, done)
             Xi = engine.half_step(CT, users, G, bias=bias, algo=algo)
             if distributed:
                 G_items = sharding.sharded_gram(Xi, ib, self.gamma, ones_col0=bias)
@@ -303,6 +331,12 @@ class WMF(RecModel):
             ev[2].record()
             if eval_d is None:
                 eval_d = self._eval_csr(eval_mat)
+            if eval_ready is not None:
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(eval_ready)
+                for t in (eval_d.indptr, eval_d.indices, eval_d.data):
+                    t.record_stream(cur)
+                eval_ready = None
             mse_eval = self._mse_device(eval_d, self.users_device[u_lo:u_hi], distributed)
             ev[3].record()
             torch.cuda.synchronize(self.device)
