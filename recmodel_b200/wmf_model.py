@@ -136,7 +136,19 @@ class WMF(RecModel):
             return np.empty((len(users), 0), dtype=items.dtype)
         cand_d = torch.from_numpy(np.ascontiguousarray(items, dtype=np.int64)).to(self.device)
         U, V = self.users_device, self.items_device
-        if k <= _lib.TOPK_MAX:
+        rank_id, world = sharding.dist_info()
+        if world > 1 and k <= _lib.TOPK_MAX and len(users) >= 1024 * world:
+            # users are independent and the item factors replicated, so every rank scores an equal
+            # slice of the users and the id lists are all-gathered (the only collective of the scoring path)
+            per = -(-len(users) // world)
+            mine = users_d[rank_id * per:(rank_id + 1) * per]
+            local = torch.zeros((per, k), dtype=torch.int64, device=self.device)
+            if mine.numel():
+                local[:mine.numel()] = engine.score_topk(mine, cand_d, U, V, k, bias=self.bias is True)
+            ids = torch.empty((world * per, k), dtype=torch.int64, device=self.device)
+            torch.distributed.all_gather_into_tensor(ids, local)
+            ids = ids[:len(users)]
+        elif k <= _lib.TOPK_MAX:
             ids = engine.score_topk(users_d, cand_d, U, V, k, bias=self.bias is True)
         else:  # very long lists: exact device scores, then a stable device sort (ties by position)
             rows = []
