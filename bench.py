@@ -163,8 +163,8 @@ def run_reference(args):
     C.data = orc.preprocess_counts(C.data, "log", ALPHA, BETA)
     CT = C.T.tocsr()
     threads = os.cpu_count() or 1
-    # bounded sample per step: ~1 % of the rows each way (a few seconds of CPU work per step)
-    frac = args.cpu_frac if args.cpu_frac else 0.01
+    # bounded sample per step: ~10 % of the rows each way (a few seconds of CPU work per step)
+    frac = args.cpu_frac if args.cpu_frac else 0.1
     for _ in range(args.warmup):
         cpu_epoch_sample(C, CT, dim, frac / 4, frac / 4, threads)
     vals, t_eps, desc = [], [], ""
@@ -317,7 +317,7 @@ def run_ours(args):
             Cp = C_host.copy()
             Cp.data = orc.preprocess_counts(Cp.data, "log", ALPHA, BETA)
             threads = os.cpu_count() or 1
-            v, _, desc = cpu_epoch_sample(Cp, Cp.T.tocsr(), dim, 0.03, 0.03, threads)
+            v, _, desc = cpu_epoch_sample(Cp, Cp.T.tocsr(), dim, 0.3, 0.3, threads)  # ~10-15 s of host work
             cpu = {"value": v, "unit": "nnz-updates/s", "cores": threads, "kind": "port", "sample": desc}
         line = {
             "metric": "wmf_nnz_updates_per_sec_per_epoch", "value": value, "unit": "nnz-updates/s", "n_gpus": world,
