@@ -240,7 +240,17 @@ def run_ours(args):
     from recmodel_b200.epoch import ResidentEpoch
     # the epoch as four replayable CUDA graphs (half-step | exchange | half-step | exchange); --no-graphs
     # launches the same sequence from Python
-    loop = ResidentEpoch(C, CT, items_d, GAMMA, bias=False, algo=algo, ub=ub, ib=ib, graphs=not args.no_graphs)
+    launch_mode = "python" if args.no_graphs else "4 CUDA graphs per epoch"
+    try:
+        loop = ResidentEpoch(C, CT, items_d, GAMMA, bias=False, algo=algo, ub=ub, ib=ib, graphs=not args.no_graphs)
+    except Exception as exc:  # graph capture refused (driver / NCCL combination): same launches issued from Python
+        if args.no_graphs:
+            raise
+        print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); launching the epoch from Python",
+              file=sys.stderr, flush=True)
+        torch.cuda.synchronize(device)
+        launch_mode = "python (graph capture failed)"
+        loop = ResidentEpoch(C, CT, items_d, GAMMA, bias=False, algo=algo, ub=ub, ib=ib, graphs=False)
     ev_pairs = []
 
     def epoch(record=False):
@@ -328,7 +338,7 @@ def run_ours(args):
                        else args.workload,
                        "l2": "inputs larger than L2 (2 x 160 MB CSR + 85 MB factors streamed per epoch)",
                        "algo": args.algo, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
-                       "launch": "python" if args.no_graphs else "4 CUDA graphs per epoch"},
+                       "launch": launch_mode},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic() if world == 1 else None,
                          "traffic_note": "DRAM read+write bytes of the same two launches (ncu --set full, profiles/); "
