@@ -45,11 +45,19 @@ namespace wmf {
 
 namespace tc {
 
+// operand stages / cp.async depth: 4 / 3 or 6 / 2 fit the 227 KB (a row holds its accumulator for its Gram and its
+// solve, so tiles staged ahead of a free accumulator shorten the Gram phase; the copies need less depth than that)
+#ifndef WMF_TC_STAGES
+#define WMF_TC_STAGES 6
+#endif
+constexpr int STAGES = WMF_TC_STAGES, STAGING = STAGES == 4 ? 3 : 2;
+static_assert(STAGES == 4 || STAGES == 6, "operand stages");
+
 constexpr int F = 128;               // factor width handled by this kernel
 constexpr int SUB = 32;              // stored entries per sub-chunk (one pipeline stage)
-constexpr int NSTAGE = 4;            // operand stages (two sub-chunks share one 128-byte-swizzled tile pair)
+constexpr int NSTAGE = STAGES;       // operand stages (two sub-chunks share one 128-byte-swizzled tile pair)
 constexpr int NTEAM = 2;             // gather teams
-constexpr int NSTG = 3;              // raw staging buffers per team (cp.async depth)
+constexpr int NSTG = STAGING;        // raw staging buffers per team (cp.async depth)
 constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 64 fp16 (K) = 16 KB, holds two sub-chunks
 constexpr int PAIR_BYTES = 2 * TILE_BYTES;   // [zh ; zl]
 constexpr int STG_BYTES = SUB * F * 4;       // 32 gathered factor rows, row-major fp32, 16 KB
@@ -422,7 +430,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         const int team = (warp - GATHER_WARP0) >> 2;
         const int m = (tid - GATHER_WARP0 * 32) & (TEAM - 1);  // feature index
         const int gw = (warp - GATHER_WARP0) & 3;              // warp within the team
-        // cursor: the team's next sub-chunk, three steps ahead of the transform
+        // cursor: the team's next sub-chunk, NSTG steps ahead of the transform
         int cu_k = -1;        // CTA-local slot of the current row
         int cu_row_n = -1;    // index of the row among this CTA's non-empty rows
         int cu_c = 0, cu_nsub = 0, cu_n = 0, cu_gi0 = 0;  // sub-chunk in row, sub-chunks / entries of the row, global index of sub-chunk 0
@@ -502,24 +510,34 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         issue(load_raw(), 0);
         advance(false);
         Desc d1 = describe();
-        issue(load_raw(), 1);
-        advance(false);
-        Desc d2 = describe();
-        Raw r2 = load_raw();
-        advance(false);
-        uint32_t j = 0;  // in iteration j the groups of sub-chunks j, j+1, j+2 are in flight: wait_group 2 completes j
+        Desc d2{-1, 0, false};
+        Raw r2;
+        if constexpr (NSTG == 3) {
+            issue(load_raw(), 1);
+            advance(false);
+            d2 = describe();
+            r2 = load_raw();
+            advance(false);
+        } else {
+            r2 = load_raw();
+            advance(false);
+        }
+        // in iteration j the copy groups of sub-chunks j .. j+NSTG-1 are in flight: wait_group NSTG-1 completes j
+        uint32_t j = 0;
         double bacc = 0.0;
         const bool prof = PROF && blockIdx.x == 0 && m == 0 && team == 0;
         long long t_empty = 0, t_bempty = 0, t_stg = 0, t_issue = 0, t_xform = 0, t_start = prof ? clock64() : 0, tt = 0, t2 = 0;
         while (d0.gi >= 0) {
             if (prof) t2 = clock64();
             const Desc d3 = describe();
-            issue(r2, (j + 2) % NSTG);   // sub-chunk j+2
-            r2 = load_raw();             // sub-chunk j+3, first touched next iteration
+            if constexpr (NSTG == 3) issue(r2, (j + 2) % 3);   // sub-chunk j+2
+            else issue(r2, (j + 1) & 1);                         // sub-chunk j+1
+            r2 = load_raw();             // the sub-chunk after that, first touched next iteration
             advance(false);
             const int s = d0.gi % NSTAGE, sb = j % NSTG;
             if (prof) { tt = clock64(); t_issue += tt - t2; }
-            asm volatile("cp.async.wait_group 2;" ::: "memory");  // this warp's copies for sub-chunk j have landed
+            if constexpr (NSTG == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");  // this warp's copies for sub-chunk j have landed
+            else asm volatile("cp.async.wait_group 1;" ::: "memory");
             __syncwarp();
             if (prof) { t2 = clock64(); t_stg += t2 - tt; }
             mbar_wait(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
@@ -579,7 +597,8 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 if (prof) t_bempty += clock64() - t2;
             }
             ++j;
-            d0 = d1; d1 = d2; d2 = d3;
+            if constexpr (NSTG == 3) { d0 = d1; d1 = d2; d2 = d3; }
+            else { d0 = d1; d1 = d3; }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         if (saw_negative) atomicOr(flags, 1);
