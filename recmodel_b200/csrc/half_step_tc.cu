@@ -6,15 +6,15 @@
 // cores with FP32-equivalent accuracy (single-pass TF32/BF16 fails the 1e-4 bar):
 //
 //   Gram    z_j = S sqrt(d_j) y_j = zh + zl, both halves FP16 (11-bit significands, like TF32, but
-//           K = 16 per instruction instead of 8); S is a power of two chosen per half-step from
-//           max diag(G) (>= max y^2) and max|d| so that zh never overflows FP16 and zl stays a normal
+//           K = 16 per instruction instead of 8); S is a power of two chosen per ROW from max diag(G)
+//           (>= max y^2) and the row's max|d| so that zh never overflows FP16 and zl stays a normal
 //           number for every entry that matters. W = sum zh zh^T + zh zl^T + zl zh^T: three
 //           tcgen05.mma (kind::f16, M = N = 128, K = 16) per 16 stored entries into a 128-column
 //           fp32 TMEM accumulator; operand tiles K-major, 128-byte swizzled.
 //   Solve   block Gauss-Jordan, the matrix STAYS in TMEM. Steps of 8 columns: every thread
 //           (= TMEM lane = matrix row) loads its 8 entries of the pivot columns (tcgen05.ld), adds G
-//           lazily; the warp that owns the 8 pivot rows factors the 8x8 pivot block (Cholesky, straight-
-//           line code) and publishes N = L^-1; every other row forms P = a N^T, updates its right-hand
+//           lazily; the warp that owns the 8 pivot rows factors the 8x8 pivot block (straight-line
+//           Cholesky in every lane, lane c then forms column c of L^-1) and publishes N = L^-1; every other row forms P = a N^T, updates its right-hand
 //           side, writes P (TF32 hi/lo split) to shared memory as an MMA operand and the rank-8 update
 //           S -= P P^T of ALL rows (above and below the pivots) is three tcgen05.mma (kind::tf32, negated
 //           A, N trimmed to the live columns). After 16 steps the system is block diagonal and
@@ -26,12 +26,16 @@
 //   warps 0-15  solve    group g = warp/4 owns accumulator g and the rows n with n % 4 == g.
 //   warps 16-23 gather   two teams of 128 threads; a team takes every other 32-entry sub-chunk of a
 //               row. Thread m owns feature m: the 32 gathered factor rows land in a raw staging buffer
-//               with cp.async (one coalesced 512-B row per warp instruction, three sub-chunks in
-//               flight per team), thread m reads column m, scales, splits to FP16 hi/lo and stores
+//               with cp.async (one coalesced 512-B row per warp instruction, two sub-chunks in flight per
+//               warp, six operand stages ahead of the MMAs), thread m reads column m, scales, splits to FP16 hi/lo and stores
 //               the K-major swizzled operand tiles a TMA load would have produced (TMA cannot: the
 //               operand is gathered, scaled and split); the rhs partial b[m] stays in registers.
 //   warp 24     MMA      one thread issues the Gram MMAs (at most two K-steps queued, so the solvers'
 //               rank-8 updates never wait behind a long burst) and commits stage/accumulator barriers.
+//
+// The tensor core truncates its fp32 accumulation, so a row with more than SPLIT_LEN entries is cut into
+// segments that different CTAs accumulate; the group that parks the last segment adds the partial Grams in
+// segment order (round-to-nearest) and solves the row (see the constants below and DESIGN.md 4.1).
 //
 // Rows whose weights are negative (sqrt undefined) or whose pivot block is not positive definite
 // raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).

@@ -124,3 +124,32 @@ def test_two_rank_gloo_sharded_epoch_equals_single(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_utils_mirror_reference_semantics():
+    """recmodel_b200.utils on the host: the split keeps the reference's RNG semantics
+    (utils.py:21-27) and test_coverage's per-user loop counts what the reference's loop counts (utils.py:3-18),
+    checked with a model whose rank is a fixed score table."""
+    from recmodel_b200 import utils
+    full = make_counts(60, 40, 600, seed=3)
+    tr, te = utils.train_test_split_sparse_mat(full, train=0.8, seed=1993)
+    np.random.seed(1993)
+    mask = np.random.rand(full.nnz) < 0.8
+    assert tr.nnz == int(mask.sum()) and te.nnz == full.nnz - tr.nnz and (tr + te != full).nnz == 0
+    assert full.nnz == 600  # the input is left alone
+
+    scores = np.random.default_rng(0).random((60, 40))
+
+    class Table:
+        def rank(self, items, users, topn=None):
+            items = np.asarray(items)
+            order = np.argsort(-scores[users, items], kind="stable")
+            return items[order][:topn]
+
+    got = utils.test_coverage(Table(), tr, 5)
+    want = np.zeros(60, dtype=np.int32)  # the reference sizes the counts by the number of users
+    for u in range(60):
+        seen = tr.indices[tr.indptr[u]:tr.indptr[u + 1]]
+        cand = np.delete(np.arange(40), seen)
+        want[cand[np.argsort(-scores[u, cand], kind="stable")][:5]] += 1
+    np.testing.assert_array_equal(got, want)
