@@ -38,8 +38,8 @@ extern "C" {
 
 /* Half-step algorithm selector */
 #define WMF_ALGO_AUTO 0
-#define WMF_ALGO_SIMT 1    /* FP32 CUDA-core Gram + Cholesky/LU; any f <= WMF_MAX_F; accuracy reference */
-#define WMF_ALGO_TCGEN05 2 /* 3xTF32 tcgen05 Gram in TMEM + FP32 solve; dim in {64,128} */
+#define WMF_ALGO_SIMT 1    /* FP32 CUDA-core Gram + Cholesky/LU; any f <= WMF_MAX_F; accuracy cross-check */
+#define WMF_ALGO_TCGEN05 2 /* whitened factors, FP16-split tcgen05 Gram + Gauss-Jordan in TMEM; f <= 256, biases included */
 
 /* Count preprocessing modes */
 #define WMF_PREPROCESS_LOG 0    /* d = alpha*log(1+beta*x)   wmf_model.py:120 */
@@ -78,31 +78,47 @@ int wmf_gram_reduce(const void* partials, int64_t n, int f, float lambda, float*
  * wmf_model.py:220-239 (recompute_factors), :337-350 (recompute_factors_bias) and the Pool
  * variants :242-309.
  *   x_r = (G + sum_j d_j y_j y_j^T)^-1  sum_j (d_j+1) y_j ,   j over the stored entries of row r
- * bias != 0: y_j has column 0 replaced by 1 and d_j = data_j - Y[j*ldy+0] (:328-343); G must
- * then come from wmf_gram(..., ones_col0=1). Rows with no entries give the zero vector
- * (:223-225; with bias solve(G,0)=0 is the same). `row_order` (nullable) is the processing
- * schedule: int32[order_len] holding every row id of [0,rows) exactly once plus any number of
- * -1 padding slots. The persistent CTAs deal its entries out round-robin (slot s goes to CTA
+ * Y has `cols` rows (the columns of the count matrix). bias != 0: y_j has column 0 replaced by 1 and
+ * d_j = data_j - Y[j*ldy+0] (:328-343); G must then come from wmf_gram(..., ones_col0=1). Rows with no
+ * entries give the zero vector (:223-225; with bias solve(G,0)=0 is the same). `row_order` (nullable) is
+ * the processing schedule: int32[order_len] holding every row id of [0,rows) exactly once plus any number
+ * of -1 padding slots. The persistent CTAs deal its entries out round-robin (slot s goes to CTA
  * s mod gridDim on the tcgen05 path, to the next free CTA on the SIMT path), so a schedule
- * built with longest rows first and heavy rows paired with light ones balances the power-law
- * tail; it never changes a row's arithmetic. X row r is written at X + r*ldx. */
-size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo);
+ * built with longest rows first balances the power-law tail; it never changes a row's arithmetic.
+ * X row r is written at X + r*ldx.
+ *
+ * WMF_ALGO_TCGEN05 (f <= 256, with or without biases; WMF_ALGO_AUTO picks it whenever it applies):
+ *   G = L L^T in double, Y~ = Y L^-T ("whitened" factors, zero padded to 128 or 256 columns), then per row
+ *   (I + sum_j d_j y~_j y~_j^T) x' = sum_j (d_j+1) y~_j on the tensor cores and x = L^-T x'. The whitened
+ *   matrix has its spectrum in [1, ~10], which makes the FP16-split tcgen05 Gram + in-TMEM Gauss-Jordan
+ *   accurate to ~1e-6 of the fp64 solution. Rows with at most wmf_als_dual_max_entries() stored entries solve
+ *   the n x n dual system (I + W W^T) u = (d+1)/sqrt(d), W = sqrt(d) y~, x' = W^T u instead (any f <= 256);
+ *   longer rows solve the f x f system on tcgen05 when f <= 128 and on the CUDA-core kernel above that.
+ *   Rows with a negative weight (possible with biases only) are solved by the CUDA-core LU kernel.
+ * WMF_ALGO_SIMT: FP32 CUDA-core Gram + Cholesky / LU with partial pivoting in the original variables;
+ *   any f <= WMF_MAX_F; accuracy cross-check and the fix-up path of the tcgen05 algorithm. */
+size_t wmf_als_half_step_workspace_bytes(int64_t rows, int64_t cols, int f, int algo);
 /* 1 if `algo` (WMF_ALGO_SIMT / WMF_ALGO_TCGEN05) handles factor width f with/without bias, else 0. */
 int wmf_als_half_step_supports(int algo, int f, int bias);
 /* The tcgen05 path cuts rows with more stored entries than this into segments that different CTAs
  * accumulate (partial Grams summed in segment order before the solve: a function of the row alone, so
  * sharding never changes a row's arithmetic). A schedule should cost such a row as that many entries. */
 int wmf_als_row_split_entries(void);
+/* Rows with at most this many stored entries take the dual (n x n) tcgen05 kernel. */
+int wmf_als_dual_max_entries(void);
 /* Workspace for a call whose long rows make `segments` segments in total: a row of n > L =
  * wmf_als_row_split_entries() stored entries makes at most ceil(n / L) of them. The plain query above
- * provides scratch for 2048 segments; a call that runs out of scratch still returns correct results
- * (the exact CUDA-core kernel redoes the half-step) but slowly. */
-size_t wmf_als_half_step_workspace_bytes_split(int64_t rows, int f, int algo, int64_t segments);
+ * provides scratch for 2048 segments; a row that finds no scratch is accumulated whole by one CTA. */
+size_t wmf_als_half_step_workspace_bytes_split(int64_t rows, int64_t cols, int f, int algo, int64_t segments);
 int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data,
-                      int64_t rows, const int32_t* row_order, int64_t order_len, const float* Y,
+                      int64_t rows, int64_t cols, const int32_t* row_order, int64_t order_len, const float* Y,
                       int64_t ldy, int f,
                       const float* G, int bias, float* X, int64_t ldx, int algo, void* ws,
                       size_t ws_bytes, void* stream);
+/* Flags of the last tcgen05 call that used `ws` (read after the stream has drained): bit 1 a pivot block
+ * failed (row re-solved by the LU kernel), bit 3 G was not positive definite (all rows solved by the LU
+ * kernel); *fixup_rows = rows the LU kernel solved. */
+int wmf_als_half_step_status(const void* ws, int* flags_host, int* fixup_rows_host, void* stream);
 
 /* K3. Fused prediction + error reduction over the non-zero stored entries of a CSR matrix:
  * replaces predict + eval_prec (wmf_model.py:205-211, base_model.py:163-176).

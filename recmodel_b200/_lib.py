@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libwmf_b200.so")
+# WMF_B200_LIB (development only): another build of the same sources, e.g. the -DWMF_WATCHDOG variant
+LIB_PATH = os.environ.get("WMF_B200_LIB") or os.path.join(_HERE, "csrc", "libwmf_b200.so")
 
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 PREPROCESS_LOG, PREPROCESS_LINEAR = 0, 1
@@ -28,12 +29,14 @@ SIGNATURES = {
     "wmf_gram_blocks": (_i64, [_i64]),
     "wmf_gram_partials": (_i32, [_p, _i64, _i64, _i64, _i32, _i64, _i32, _p, _sz, _p]),
     "wmf_gram_reduce": (_i32, [_p, _i64, _i32, _f32, _p, _p]),
-    "wmf_als_half_step_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "wmf_als_half_step_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "wmf_als_dual_max_entries": (_i32, []),
+    "wmf_als_half_step_status": (_i32, [_p, _p, _p, _p]),
     "wmf_als_half_step_supports": (_i32, [_i32, _i32, _i32]),
     "wmf_rank_ahead": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _p, _p]),
     "wmf_als_row_split_entries": (_i32, []),
-    "wmf_als_half_step_workspace_bytes_split": (_sz, [_i64, _i32, _i32, _i64]),
-    "wmf_als_half_step": (_i32, [_p, _p, _p, _i64, _p, _i64, _p, _i64, _i32, _p, _i32, _p, _i64, _i32, _p, _sz, _p]),
+    "wmf_als_half_step_workspace_bytes_split": (_sz, [_i64, _i64, _i32, _i32, _i64]),
+    "wmf_als_half_step": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _i32, _p, _i32, _p, _i64, _i32, _p, _sz, _p]),
     "wmf_sddmm_loss_workspace_bytes": (_sz, [_i64]),
     "wmf_sddmm_loss": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "wmf_predict_pairs": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i32, _i32, _p, _p]),

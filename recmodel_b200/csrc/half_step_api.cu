@@ -22,30 +22,41 @@ int wmf_als_half_step_supports(int algo, int f, int bias) {
     return (algo == WMF_ALGO_SIMT || algo == WMF_ALGO_AUTO) ? 1 : 0;
 }
 
-static size_t half_step_workspace(int64_t rows, int f, int algo, int64_t segments) {
-    if (f <= 0 || f > WMF_MAX_F) return 0;
+int wmf_als_dual_max_entries(void) { return tc_dual_max_entries(); }
+
+static size_t half_step_workspace(int64_t rows, int64_t cols, int f, int algo, int64_t segments) {
+    if (f <= 0 || f > WMF_MAX_F || rows < 0 || cols < 0) return 0;
     size_t a = simt_half_step_workspace_bytes(f);
     size_t b = 0;
-    if (algo != WMF_ALGO_SIMT) {
-        size_t b0 = tc_half_step_supported(f, 0) ? tc_half_step_workspace_bytes(rows, f, 0, segments) : 0;
-        size_t b1 = tc_half_step_supported(f, 1) ? tc_half_step_workspace_bytes(rows, f, 1, segments) : 0;
-        b = b0 > b1 ? b0 : b1;
-    }
+    if (algo != WMF_ALGO_SIMT && tc_half_step_supported(f, 0)) b = tc_half_step_workspace_bytes(rows, cols, f, 0, segments);
     return a > b ? a : b;
 }
 
-size_t wmf_als_half_step_workspace_bytes(int64_t rows, int f, int algo) { return half_step_workspace(rows, f, algo, -1); }
-
-size_t wmf_als_half_step_workspace_bytes_split(int64_t rows, int f, int algo, int64_t segments) {
-    return half_step_workspace(rows, f, algo, segments < 0 ? 0 : segments);
+size_t wmf_als_half_step_workspace_bytes(int64_t rows, int64_t cols, int f, int algo) {
+    return half_step_workspace(rows, cols, f, algo, -1);
 }
 
-int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows,
+size_t wmf_als_half_step_workspace_bytes_split(int64_t rows, int64_t cols, int f, int algo, int64_t segments) {
+    return half_step_workspace(rows, cols, f, algo, segments < 0 ? 0 : segments);
+}
+
+int wmf_als_half_step_status(const void* ws, int* flags_host, int* fixup_rows_host, void* stream) {
+    WMF_REQUIRE(ws != nullptr, "wmf_als_half_step_status: null workspace");
+    int hdr[9];
+    WMF_CUDA(cudaMemcpyAsync(hdr, ws, sizeof(hdr), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    WMF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flags_host) *flags_host = hdr[1];
+    if (fixup_rows_host) *fixup_rows_host = hdr[8];
+    return WMF_OK;
+}
+
+int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows, int64_t cols,
                       const int32_t* row_order, int64_t order_len, const float* Y, int64_t ldy, int f,
                       const float* G, int bias,
                       float* X, int64_t ldx, int algo, void* ws, size_t ws_bytes, void* stream) {
     WMF_REQUIRE(f > 0 && f <= WMF_MAX_F && (!bias || f >= 2), "wmf_als_half_step: f=%d outside 1..%d", f, WMF_MAX_F);
     WMF_REQUIRE(rows >= 0 && rows < (1ll << 31), "wmf_als_half_step: rows=%lld out of range", (long long)rows);
+    WMF_REQUIRE(cols >= 0 && cols < (1ll << 31), "wmf_als_half_step: cols=%lld out of range", (long long)cols);
     if (rows == 0) return WMF_OK;
     WMF_REQUIRE(indptr && Y && G && X && ldy >= f && ldx >= f, "wmf_als_half_step: null pointer or short leading dimension");
     WMF_REQUIRE(algo == WMF_ALGO_AUTO || algo == WMF_ALGO_SIMT || algo == WMF_ALGO_TCGEN05,
@@ -55,10 +66,10 @@ int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float
     WMF_REQUIRE(row_order == nullptr || order_len >= rows, "wmf_als_half_step: schedule shorter than rows");
     p.indptr = indptr; p.indices = indices; p.data = data; p.rows = rows; p.row_order = row_order;
     p.sched_len = row_order ? order_len : rows;
-    p.Y = Y; p.ldy = ldy; p.f = f; p.G = G; p.bias = bias; p.X = X; p.ldx = ldx;
+    p.Y = Y; p.ldy = ldy; p.f = f; p.G = G; p.bias = bias; p.X = X; p.ldx = ldx; p.cols = cols;
     if (chosen == WMF_ALGO_TCGEN05) {
         if (!tc_half_step_supported(f, bias)) {
-            set_error("wmf_als_half_step: tcgen05 path takes dim in {64,128} (f=%d, bias=%d)", f, bias);
+            set_error("wmf_als_half_step: the tcgen05 path takes f <= 256 (f=%d, bias=%d)", f, bias);
             return WMF_ERR_UNSUPPORTED;
         }
         return tc_half_step(p, ws, ws_bytes, (cudaStream_t)stream);

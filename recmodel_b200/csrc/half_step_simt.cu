@@ -40,13 +40,14 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
     const int T = FP / 4;
     const int ntiles = T * (T + 1) / 2;
     if (p.run_if != nullptr && *p.run_if == 0) return;  // fix-up launch with nothing to fix
+    const int64_t sched_len = p.sched_len_dev ? (int64_t)*p.sched_len_dev : p.sched_len;  // device-side fix-up list
 
     while (true) {
         if (tid == 0) misc[0] = atomicAdd(p.counter, 1);
         __syncthreads();
         const int64_t r = misc[0];
         __syncthreads();
-        if (r >= p.sched_len) break;
+        if (r >= sched_len) break;
         const int64_t row = p.row_order ? p.row_order[r] : r;
         if (row < 0) continue;  // padding slot of a balanced schedule
         const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
@@ -191,7 +192,7 @@ int simt_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStre
     }
     HalfStepParams p = in;
     p.counter = reinterpret_cast<int*>(ws);
-    const bool fixup = in.run_if != nullptr;  // header already initialised by the caller
+    const bool fixup = in.run_if != nullptr || in.sched_len_dev != nullptr;  // header already initialised by the caller
     p.slab = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256);
     p.lda = pl.lda;
     p.FP = pl.FP;

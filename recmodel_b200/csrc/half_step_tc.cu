@@ -39,10 +39,10 @@
 //
 // Rows whose weights are negative (sqrt undefined) or whose pivot block is not positive definite
 // raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).
-#include <cuda_fp16.h>
 #include <stdlib.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "half_step.cuh"
+#include "whiten.cuh"
 #include "factor8.cuh"
 
 namespace wmf {
@@ -99,260 +99,141 @@ constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                // + slack f
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_GROUPS % 128 == 0 && GROUP_BYTES % 128 == 0 && OFF_BARS % 8 == 0 && OFF_STG % 1024 == 0, "alignment");
 
-// workspace layout (bytes): [0] SIMT row counter, [4] redo flags, [8] max diag(G), [16] total slots,
-// [20] split rows, [24] partial slots, [28] extra slots, [256, 768) profile slots, [1024, ...) row table,
-// split table, split-row counters, partial-Gram scratch
+// workspace layout: see TcLayout below
 constexpr size_t WS_PROF = 256, WS_TABLES = 1024;
-// Rows longer than this are cut into segments of at most this many entries. Two reasons: (1) balance, a row
-// never costs its CTA more than one segment; (2) accuracy: the tensor core TRUNCATES its fp32 accumulation
-// (scripts/probe/mma_round_probe.cu), a bias of ~half an ulp per MMA that grows with the number of MMAs into
-// one accumulator. Measured on the heaviest item rows at ML-20M shape (scripts/long_row_accuracy.py, error of
-// the solution against fp64; the reference's own fp32 arithmetic is 1.3e-5 there): segments of 8192 entries
-// 1.3e-4, 4096 6.2e-5, 2048 2.9e-5, 1024 1.3e-5, 512 5e-6, against 3.75 / 3.76 / 3.85 / 4.26 / 5.1 ms for the
-// item half-step (every segment parks 64 KB in L2/HBM). The segment partials are summed with
-// round-to-nearest FP32 adds in segment order. WMF_TC_SPLIT overrides the length (experiments).
+// Rows longer than this are cut into segments of at most this many entries, for balance (a row never costs its
+// CTA more than one segment) and for accuracy: the tensor core TRUNCATES its fp32 accumulation
+// (scripts/probe/mma_round_probe.cu), a bias of ~half an ulp per MMA that grows with the number of MMAs into one
+// accumulator. The segment partials are summed with round-to-nearest FP32 adds in segment order by the group that
+// parks the last one. Environment knobs, read once per process (experiments; the defaults are the product):
+//   WMF_TC_SPLIT=<entries>   segment length (default 2048)
+//   WMF_TC_DUAL=0            send short rows to the primal kernel as well (dual kernel off)
+//   WMF_TC_PROFILE=1         per-role cycle counters of CTA 0 (only in a -DWMF_TC_PROFILE_BUILD library)
 constexpr int SPLIT_LEN_DEFAULT = 2048;
+static int env_int_once(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static int split_len() {
-    static int v = 0;
-    if (v == 0) { const char* e = getenv("WMF_TC_SPLIT"); v = e ? atoi(e) : SPLIT_LEN_DEFAULT; if (v < 64) v = SPLIT_LEN_DEFAULT; v = (v + 31) / 32 * 32; }
+    static const int v = [] { int x = env_int_once("WMF_TC_SPLIT", SPLIT_LEN_DEFAULT); if (x < 64) x = SPLIT_LEN_DEFAULT; return (x + 31) / 32 * 32; }();
     return v;
+}
+static bool dual_enabled() { static const bool v = env_int_once("WMF_TC_DUAL", 1) != 0; return v; }
+static bool profile_enabled() {
+#ifdef WMF_TC_PROFILE_BUILD
+    static const bool v = env_int_once("WMF_TC_PROFILE", 0) != 0;
+    return v;
+#else
+    return false;
+#endif
 }
 constexpr int DEFAULT_PARTS = 2048;  // partial slots the legacy workspace query (rows only) provides
 constexpr size_t PART_FLOATS = (size_t)F * F + F;  // a segment's S^2 W (chunk-major) and its rhs partial
-struct __align__(16) RowEnt {
-    int32_t row;   // CSR row id, -1 = padding slot
-    int32_t n;     // stored entries (0: nothing to do, X row already zeroed)
-    int64_t lo;    // indptr[row] (48 bits when packed in the table)
-    int32_t sexp;  // S = 2^sexp for this row (the table packs it into bits 16-23 of the last word)
-    int32_t part;  // >= 0: this entry is a segment of a split row; index of its record in the split table (bits 24-31 flag)
-};
-// second table, one 16-byte record per segment of a split row
-struct __align__(16) SegEnt {
-    int32_t split_id;    // counter slot of the row
-    int32_t nseg;        // segments of the row
-    int32_t first_part;  // scratch slot of segment 0 (segments are consecutive)
-    int32_t seg;         // this segment's index
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of
-// re-polling every ~50 cycles (polling was 30 % of all issued instructions, ncu r01b)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
-}
-// K-major, no swizzle: 8-row x 16-byte core matrices; the two K-chunks of a row group are
-// LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart (panel operand, K = 8 fp32).
-__device__ __forceinline__ uint64_t umma_desc_panel(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
-           (1ull << 46);
-}
-// cute::UMMA::InstrDescriptor: fp32 accumulate (bit 4), A/B formats at bits 7/10 (0 = F16, 2 = TF32),
-// bit 13 negates A, N >> 3 at bit 17, M >> 4 at bit 24; K-major A and B.
-constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t IDESC_TF32_NEG_M128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((128u >> 4) << 24);  // N filled in at issue
-#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-// round-to-nearest (ties away) to the 10-bit TF32 mantissa, done with integer ops
-__device__ __forceinline__ float tf32_round(float x) {
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
-                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-                 : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {  // arrive when this thread's copies have landed
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-// explicit shared-space accesses (generic ld/st on pointers derived from the aligned base cost an
-// address-space check per access)
-__device__ __forceinline__ float4 lds4(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ float lds1(uint32_t a) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts4(uint32_t a, float x, float y, float z, float w) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-__device__ __forceinline__ void sts4u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ void sts1(uint32_t a, float x) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
-}
-__device__ __forceinline__ void named_bar(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-
-// S = 2^e with S * sqrt(max diag G) * sqrt(max|d| of the row) just below the FP16 maximum. diag(G) = sum y^2 +
-// lambda bounds every y^2, so zh cannot overflow; the bound is loose by up to sqrt(#rows of Y), which
-// only moves the point below which zl becomes subnormal (entries that small do not matter). The scale is
-// per ROW (not per call) so that a row's arithmetic does not depend on which rows share its launch:
-// row-sharded runs stay bitwise equal to single-GPU runs.
-__device__ __forceinline__ int gram_scale_exp(float max_diag_g, float max_d) {
-    const float m = sqrtf(max_diag_g) * sqrtf(max_d);
-    if (!(m > 0.0f) || !(m < 3.0e38f)) return 0;
-    int e = (int)floorf(log2f(60000.0f / m));
-    return e > 40 ? 40 : (e < -40 ? -40 : e);  // S^2 and 1/S^2 stay finite
-}
-
 // ---------------------------------------------------------------------------------------------------
-// prep: row table (one 16-byte entry per schedule slot), zero rows without entries, and the maxima
-// that fix the FP16 scale.
+// prep: the schedule tables (one 16-byte entry per slot and kernel), the per-row FP16 scale, zero rows
+// without entries, and the fix-up list.
 // ---------------------------------------------------------------------------------------------------
-// One warp per schedule slot: row table entry, per-row FP16 scale, zero fill of rows without entries.
+// One warp per schedule slot. A row goes to exactly one place:
+//   no stored entries              -> its whitened solution is zeroed here (wmf_model.py:223-225)
+//   a negative weight (bias formula, d~ = d - beta, wmf_model.py:343), or G itself not positive definite
+//                                  -> fix-up list: the CUDA-core LU kernel solves it after the tensor-core kernels
+//   at most nd_max entries         -> dual table (half_step_dual.cu: n x n system)
+//   otherwise                      -> primal table (this file: f x f system); wider than 128 features there is no
+//                                     primal tensor-core kernel yet and the row joins the fix-up list
 // Rows longer than SPLIT_LEN are cut into equal segments (a function of the row length only, so a row's
 // arithmetic never depends on the launch it is in): segment 0 stays in the row's slot, the others go to
 // extra slots behind the schedule, which the persistent CTAs reach round-robin like every other slot.
 __global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, int4* __restrict__ segtab,
-                                    uint32_t* __restrict__ hdr_u, int64_t extra_slot0, int max_extra, int max_parts, int SPLIT_LEN) {
+                                    int4* __restrict__ dtab, uint32_t* __restrict__ hdr_u, int64_t extra_slot0,
+                                    int max_extra, int max_parts, int SPLIT_LEN, int primal_ok) {
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= p.sched_len) return;
     const int64_t row = p.row_order ? p.row_order[s] : s;
-    int4 e = make_int4(-1, 0, 0, 0);
+    int4 e = make_int4(-1, 0, 0, 0), de = make_int4(-1, 0, 0, 0);
     if (row >= 0) {
         const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-        const int64_t n = hi - lo;
+        int64_t n = hi - lo;
         float m = 0.0f;
-        for (int64_t i = lo + lane; i < hi; i += 32) m = fmaxf(m, fabsf(__ldg(p.data + i)));
+        bool neg = false, zero = false;
+        for (int64_t i = lo + lane; i < hi; i += 32) {
+            float d = __ldg(p.data + i);
+            if (p.bias) d = __fsub_rn(d, __ldg(p.Yraw + (int64_t)__ldg(p.indices + i) * p.ldraw));
+            neg |= !(d >= 0.0f);   // NaN weights go to the LU kernel too
+            zero |= d == 0.0f;
+            m = fmaxf(m, fabsf(d));
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        neg = __any_sync(0xffffffffu, neg);
+        zero = __any_sync(0xffffffffu, zero);
+        const bool g_bad = (hdr_u[1] & 8u) != 0;
+        // the dual right-hand side (d+1)/sqrt(d) needs d > 0: a stored zero weight (it still adds y to the
+        // right-hand side, wmf_model.py:239) keeps the row on the primal side
+        const bool dual = n > 0 && n <= p.nd_max && !zero;
+        if (n > 0 && (neg || g_bad || (!dual && !primal_ok))) {
+            if (lane == 0) p.fix_list[atomicAdd(p.fix_count, 1)] = (int)row;
+            n = -1;  // neither kernel touches it; the unwhitening pass writes zeros that the LU kernel overwrites
+        }
         const int sexp = gram_scale_exp(__uint_as_float(hdr_u[2]), m);
         const uint32_t sbits = (uint32_t)(sexp + 64) << 16;
-        // equal segments of whole sub-chunks, none empty (a function of the row length alone)
-        int nseg = 1;
-        int64_t seg_len = n;
-        if (n > SPLIT_LEN) {
-            const int64_t want = (n + SPLIT_LEN - 1) / SPLIT_LEN;
-            seg_len = ((n + want - 1) / want + SUB - 1) / SUB * SUB;
-            nseg = (int)((n + seg_len - 1) / seg_len);
-        }
-        int split_id = 0, first_part = 0, extra_base = 0;
-        if (nseg > 1) {
-            if (lane == 0) {
-                split_id = (int)atomicAdd(hdr_u + 5, 1u);
-                first_part = (int)atomicAdd(hdr_u + 6, (uint32_t)nseg);
-                extra_base = (int)atomicAdd(hdr_u + 7, (uint32_t)(nseg - 1));
-            }
-            split_id = __shfl_sync(0xffffffffu, split_id, 0);
-            first_part = __shfl_sync(0xffffffffu, first_part, 0);
-            extra_base = __shfl_sync(0xffffffffu, extra_base, 0);
-            if (2 * split_id + 2 > max_parts || first_part + nseg > max_parts || extra_base + nseg - 1 > max_extra) {
-                nseg = 1;  // out of scratch: the row stays whole here and the accurate SIMT kernel redoes the half-step
-                if (lane == 0) atomicOr(reinterpret_cast<int*>(hdr_u) + 1, 4);
-            }
-        }
-        e.x = (int32_t)row;
-        if (nseg == 1) {
-            e.y = (int32_t)n;
-            e.z = (int32_t)(uint32_t)lo;
-            e.w = (int32_t)((uint32_t)((lo >> 32) & 0xFFFF) | sbits);
-            if (n == 0) {  // wmf_model.py:223-225
-                float4* x = reinterpret_cast<float4*>(p.X + row * p.ldx);
-                if ((p.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0) x[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-                else for (int i = lane; i < F; i += 32) p.X[row * p.ldx + i] = 0.0f;
-            }
+        e.x = de.x = (int32_t)row;
+        if (n <= 0) {
+            float4* x = reinterpret_cast<float4*>(p.X + row * p.ldx);  // whitened solution: ld = FP, 16-byte aligned
+            for (int i = lane; i < p.FP / 4; i += 32) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (dual) {
+            de.y = (int32_t)n;
+            de.z = (int32_t)(uint32_t)lo;
+            de.w = (int32_t)((uint32_t)((lo >> 32) & 0xFFFF) | sbits);
         } else {
-            for (int k = lane; k < nseg; k += 32) {
-                const int64_t slo = lo + (int64_t)k * seg_len;
-                const int64_t shi = slo + seg_len < hi ? slo + seg_len : hi;
-                int4 se;
-                se.x = (int32_t)row;
-                se.y = (int32_t)(shi > slo ? shi - slo : 0);
-                se.z = (int32_t)(uint32_t)slo;
-                se.w = (int32_t)((uint32_t)((slo >> 32) & 0xFFFF) | sbits | 0x80000000u);  // bit 31: segment of a split row
-                const int64_t slot = k == 0 ? s : extra_slot0 + extra_base + (k - 1);
-                tab[slot] = se;
-                segtab[slot] = make_int4(split_id, nseg, first_part, k);
+            // equal segments of whole sub-chunks, none empty (a function of the row length alone)
+            int nseg = 1;
+            int64_t seg_len = n;
+            if (n > SPLIT_LEN) {
+                const int64_t want = (n + SPLIT_LEN - 1) / SPLIT_LEN;
+                seg_len = ((n + want - 1) / want + SUB - 1) / SUB * SUB;
+                nseg = (int)((n + seg_len - 1) / seg_len);
             }
-            return;
+            int split_id = 0, first_part = 0, extra_base = 0;
+            if (nseg > 1) {
+                if (lane == 0) {
+                    split_id = (int)atomicAdd(hdr_u + 5, 1u);
+                    first_part = (int)atomicAdd(hdr_u + 6, (uint32_t)nseg);
+                    extra_base = (int)atomicAdd(hdr_u + 7, (uint32_t)(nseg - 1));
+                }
+                split_id = __shfl_sync(0xffffffffu, split_id, 0);
+                first_part = __shfl_sync(0xffffffffu, first_part, 0);
+                extra_base = __shfl_sync(0xffffffffu, extra_base, 0);
+                if (2 * split_id + 2 > max_parts || first_part + nseg > max_parts || extra_base + nseg - 1 > max_extra)
+                    nseg = 1;  // out of scratch: the row stays whole (its CTA carries it alone; accuracy is unaffected
+                               // at these lengths since the factors are whitened)
+            }
+            if (nseg == 1) {
+                e.y = (int32_t)n;
+                e.z = (int32_t)(uint32_t)lo;
+                e.w = (int32_t)((uint32_t)((lo >> 32) & 0xFFFF) | sbits);
+            } else {
+                for (int k = lane; k < nseg; k += 32) {
+                    const int64_t slo = lo + (int64_t)k * seg_len;
+                    const int64_t shi = slo + seg_len < hi ? slo + seg_len : hi;
+                    int4 se;
+                    se.x = (int32_t)row;
+                    se.y = (int32_t)(shi > slo ? shi - slo : 0);
+                    se.z = (int32_t)(uint32_t)slo;
+                    se.w = (int32_t)((uint32_t)((slo >> 32) & 0xFFFF) | sbits | 0x80000000u);  // bit 31: segment of a split row
+                    const int64_t slot = k == 0 ? s : extra_slot0 + extra_base + (k - 1);
+                    tab[slot] = se;
+                    segtab[slot] = make_int4(split_id, nseg, first_part, k);
+                }
+                if (lane == 0) dtab[s] = de;
+                return;
+            }
         }
     }
-    if (lane == 0) tab[s] = e;
+    if (lane == 0) { tab[s] = e; dtab[s] = de; }
 }
 
 // total slots = schedule (rounded up to a multiple of the grid) + extra segment slots
 __global__ void tc_finish_prep_kernel(uint32_t* __restrict__ hdr_u, int64_t extra_slot0, int max_extra) {
     const uint32_t extra = hdr_u[7] < (uint32_t)max_extra ? hdr_u[7] : (uint32_t)max_extra;
     hdr_u[4] = (uint32_t)(extra_slot0 + extra);
-}
-
-// hdr[2] = max diag(G)
-__global__ void tc_maxima_kernel(HalfStepParams p, float* __restrict__ hdr) {
-    float m = 0.0f;
-    for (int i = threadIdx.x; i < F; i += 32) m = fmaxf(m, fabsf(p.G[i * F + i]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) hdr[2] = m;
 }
 
 }  // namespace tc
@@ -418,10 +299,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         RowEnt e{-1, 0, 0, 0, -1};
         if (k < nslots) {
             const int slot = k * ts + (k < nextra ? base_x : base_s);
-            const int4 v = __ldg(rowtab + slot);
-            e.row = v.x; e.n = v.y; e.lo = ((int64_t)(uint32_t)v.z) | ((int64_t)(v.w & 0xFFFF) << 32);
-            e.sexp = (int)(((uint32_t)v.w >> 16) & 0xFFu) - 64;
-            e.part = (v.w < 0) ? slot : -1;  // segment of a split row: its record sits at the same slot of the split table
+            e = unpack_ent(__ldg(rowtab + slot), slot);  // a segment's record sits at the same slot of the split table
         }
         return e;
     };
@@ -474,13 +352,16 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         // Every gather warp is its own pipeline: it stages the 32-feature slice (128 B) of the 32 factor rows that
         // its lanes will read, so nothing but the operand-stage barriers is shared inside a team.
         struct Raw { int idx; float d; float s; };
-        bool saw_negative = false;
         const int wbuf0 = ((team * 4 + gw) * NSTG);  // this warp's first staging / meta buffer
         auto load_raw = [&]() {  // lane l: entry l of the cursor's sub-chunk
             Raw rw{-1, 0.f, cu_S};
             if (cu_k < nslots) {
                 const int off = cu_c * SUB + lane;
-                if (off < cu_n) { rw.d = __ldg(p.data + cu_lo + off); rw.idx = __ldg(p.indices + cu_lo + off); }
+                if (off < cu_n) {
+                    rw.d = __ldg(p.data + cu_lo + off);
+                    rw.idx = __ldg(p.indices + cu_lo + off);
+                    if (p.bias) rw.d = __fsub_rn(rw.d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
+                }
             }
             return rw;
         };
@@ -489,9 +370,8 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
             __syncwarp();  // the buffer's previous contents have been read by every lane
             {
                 float sq = 0.f, dp1 = 0.f;
-                if (rw.idx >= 0) {
-                    if (rw.d < 0.f) saw_negative = true;
-                    sq = rw.s * sqrtf(fabsf(rw.d));
+                if (rw.idx >= 0) {  // rows with a negative weight never get here (fix-up list, tc_prep_rows_kernel)
+                    sq = rw.s * sqrtf(rw.d);
                     dp1 = __fadd_rn(rw.d, 1.0f);
                 }
                 const uint32_t ma = smem_base + OFF_META + wb * META_BYTES + lane * 4;
@@ -605,7 +485,6 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
             else { d0 = d1; d1 = d3; }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-        if (saw_negative) atomicOr(flags, 1);
         if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = j; p.prof[5] = t_stg; p.prof[11] = t_issue; p.prof[12] = t_xform; }
     } else if (warp == MMA_WARP) {
         // =============================== GRAM MMA ISSUE ===============================
@@ -625,6 +504,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 if (prof) t_accempty += clock64() - tt;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
+                const uint32_t idesc_gram = IDESC_F16_M128 | ((uint32_t)(p.f16 >> 3) << 17);  // N = live columns
                 uint32_t accumulate = 0;
                 for (int base = 0; base < e.n; base += SUB, ++gi) {
                     const int s = gi % NSTAGE;
@@ -644,9 +524,9 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                     for (int kk = 0; kk < nk; ++kk) {
                         // advance 16 fp16 = 32 B along K inside the 128-B swizzle row
                         const uint64_t hk = dh + (uint64_t)(kk * 2), lk = dl + (uint64_t)(kk * 2);
-                        umma_f16(d_tmem, hk, hk, IDESC_F16_M128_N128, accumulate);  // zh zh^T
-                        umma_f16(d_tmem, hk, lk, IDESC_F16_M128_N128, 1u);          // zh zl^T
-                        umma_f16(d_tmem, lk, hk, IDESC_F16_M128_N128, 1u);          // zl zh^T
+                        umma_f16(d_tmem, hk, hk, idesc_gram, accumulate);  // zh zh^T
+                        umma_f16(d_tmem, hk, lk, idesc_gram, 1u);          // zh zl^T
+                        umma_f16(d_tmem, lk, hk, idesc_gram, 1u);          // zl zh^T
                         accumulate = 1;
                     }
                     tc_commit(bar_empty(s));
@@ -670,7 +550,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * F);
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
-        const float* Gcol = p.G + t;  // G is symmetric: G[t][c] = G[c][t], and column t is coalesced across the warp
+        const int f8 = p.f8, f16 = p.f16;  // live width: the whitened system is the identity beyond it
         uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
@@ -696,7 +576,6 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 if (t0 == 1 || both) { mbar_wait(bar_b_full(g, 1), cnt_b1 & 1u); ++cnt_b1; bB = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 1) * F + t) * 4); }
                 bt = bA + bB;
             }
-            float dbg_val = bt;
             mbar_arrive(bar_b_empty(g));
             mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
             tc_fence_after();
@@ -707,7 +586,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 const int4 sg = __ldg(segtab + e.part);  // split_id, nseg, first_part, seg
                 float* mine = parts + (size_t)(sg.z + sg.w) * PART_FLOATS;
 #pragma unroll 1
-                for (int c0 = 0; c0 < F; c0 += NB) {
+                for (int c0 = 0; c0 < f8; c0 += NB) {
                     float a[NB];
                     tmem_ld8(t_row + c0, a);
                     float4* dst = reinterpret_cast<float4*>(mine + (c0 >> 3) * (F * NB) + t * NB);
@@ -729,7 +608,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 __threadfence();
                 const float* first = parts + (size_t)sg.z * PART_FLOATS;
 #pragma unroll 1
-                for (int c0 = 0; c0 < F; c0 += NB) {
+                for (int c0 = 0; c0 < f8; c0 += NB) {
                     float a[NB] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     for (int k2 = 0; k2 < sg.y; ++k2) {
                         const float4* src = reinterpret_cast<const float4*>(first + (size_t)k2 * PART_FLOATS + (c0 >> 3) * (F * NB) + t * NB);
@@ -746,10 +625,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 tc_fence_after();
             }
 #pragma unroll 1
-            for (int c0 = 0; c0 < F; c0 += NB) {
-                float gg[NB];
-#pragma unroll
-                for (int i = 0; i < NB; ++i) gg[i] = __ldg(Gcol + (c0 + i) * F);
+            for (int c0 = 0; c0 < f8; c0 += NB) {
                 if (prof) t3 = clock64();
                 if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
                     mbar_wait(bar_panel(g), panel_n & 1u);
@@ -759,15 +635,14 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 if (prof) { t4 = clock64(); ph_wait += t4 - t3; }
                 float a[NB];
                 tmem_ld8(t_row + c0, a);
-                if (c0 + NB == F) {  // last read of the accumulator: the Gram of this group's next row may start
+                if (c0 + NB == f8) {  // last read of the accumulator: the Gram of this group's next row may start
                     tc_fence_before();
                     mbar_arrive(bar_acc_empty(g));
                 }
-#pragma unroll
-                for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, gg[i]);
-                if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
-                if (p.KC >= 2 && c0 == ((p.KC - 2) >> 3) * 8) dbg_val = a[(p.KC - 2) & 7];  // debug: column KC-2 of A
                 const int rel = t - c0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, rel == i ? 1.0f : 0.0f);  // I + sum d y~ y~^T
+                if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
                 const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
                 if (q == (c0 >> 5)) {
                     // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
@@ -808,7 +683,11 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                     if (lane == 0) {
                         sts4(zd, inv_s * z[0], inv_s * z[1], inv_s * z[2], inv_s * z[3]);
                         sts4(zd + 16, inv_s * z[4], inv_s * z[5], inv_s * z[6], inv_s * z[7]);
-                        if (!ok) atomicOr(flags, 2);  // not positive definite: the SIMT/LU kernel redoes the half-step
+                        if (!ok) {  // cannot happen with non-negative weights (spectrum >= 1); a numerical accident
+                                    // sends the row to the LU kernel and leaves a host-visible mark
+                            atomicOr(flags, 2);
+                            p.fix_list[atomicAdd(p.fix_count, 1)] = e.row;
+                        }
                     }
                     if (prof) { t4 = clock64(); ph_own += t4 - t3; }
                 }
@@ -845,7 +724,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                     u0 = fmaf(P[6], z1.z, u0); u1 = fmaf(P[7], z1.w, u1);
                     bt -= u0 + u1;
                 }
-                if (c0 + NB < F) {
+                if (c0 + NB < f8) {
                     float lh[NB], ll[NB];
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
@@ -866,7 +745,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                         tc_fence_after();
                         if (prof) { t4 = clock64(); ph_p += t4 - t3; }
                         const uint32_t start = (uint32_t)((c0 + NB) >> 4) << 4;
-                        const uint32_t idesc = IDESC_TF32_NEG_M128 | (((F - start) >> 3) << 17);
+                        const uint32_t idesc = IDESC_TF32_NEG_M128 | ((((uint32_t)f16 - start) >> 3) << 17);
                         const uint64_t bH = descH + (uint64_t)(start * 2), bL = descL + (uint64_t)(start * 2);
                         umma_tf32(d_tmem + start, descH, bH, idesc, 1u);
                         umma_tf32(d_tmem + start, descH, bL, idesc, 1u);
@@ -898,7 +777,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                     for (int kk = 0; kk <= jj; ++kk) nsel = (kk == r8) ? nr[kk] : nsel;
                     xt = fmaf(nsel, y, xt);
                 }
-                xout[t] = p.KC ? dbg_val : xt * inv_s2;  // N was stored as S N
+                xout[t] = t < f8 ? xt * inv_s2 : 0.0f;  // N was stored as S N; padding columns of the whitened solution are 0
             }
             named_bar(bar_id, GROUP);  // Nst / bfin are rewritten by the next row
             if (prof) t_back += clock64() - tt;
@@ -918,30 +797,50 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
     }
 }
 
-bool tc_half_step_supported(int f, int bias) { return f == tc::F && !bias; }
+// f <= 256: every width goes through the whitened pipeline (factors padded to 128 or 256 columns). Rows with at
+// most tc_dual_max_entries() stored entries take the dual kernel at any width; longer rows take the primal kernel
+// of this file when f <= 128 and the CUDA-core kernel above that. Biases are a shifted weight (wmf_model.py:343).
+bool tc_half_step_supported(int f, int bias) { return f >= 1 && f <= 256 && (!bias || f >= 2); }
 
-// Workspace: header, row table + split table (32 bytes per slot), split-row counters, partial-Gram scratch
-// for the segments of split rows (f = 128 needs no SIMT slab). Schedules of up to 2*rows + 4096 slots fit.
+// Workspace (bytes from a 256-aligned base):
+//   [0, 1024)   header: [1] flags (1 unused, 2 failed pivot, 8 G not positive definite), [2] max y~^2 (float bits),
+//               [4] total slots, [5] split rows, [6] partial slots, [7] extra slots, [8] fix-up rows; [256, 768) profile
+//   tables      primal row table + split table (32 B per slot), dual row table (16 B per slot), split-row counters,
+//               fix-up list (4 B per row)
+//   whitening   double scratch of the Cholesky, the two FP x FP multipliers, Y~ (cols x FP), X' (rows x FP)
+//   simt        the CUDA-core kernel's own workspace (fix-up rows)
+//   parts       partial-Gram scratch for the segments of split rows: whatever is left
 struct TcLayout {
     int64_t cap_slots, max_parts;
-    size_t off_tab, off_seg, off_cnt, off_parts, total;
+    size_t off_tab, off_seg, off_dtab, off_cnt, off_fix, zero_end, off_chol, off_mw, off_mu, off_yt, off_xp, off_simt,
+        off_parts, total;
 };
-static TcLayout tc_layout(int64_t sched_slots, int64_t parts) {
+static int tc_fp(int f) { return f <= 128 ? 128 : 256; }
+static TcLayout tc_layout(int64_t sched_slots, int64_t rows, int64_t cols, int f, int64_t parts) {
     TcLayout L;
+    const size_t FP = (size_t)tc_fp(f);
     L.max_parts = parts < 2 ? 0 : parts;
     L.cap_slots = sched_slots + L.max_parts;
     L.off_tab = WS_TABLES;
     L.off_seg = L.off_tab + 16 * (size_t)L.cap_slots;
-    L.off_cnt = L.off_seg + 16 * (size_t)L.cap_slots;
-    L.off_parts = (L.off_cnt + 4 * (size_t)(L.max_parts / 2 + 1) + 255) / 256 * 256;
+    L.off_dtab = L.off_seg + 16 * (size_t)L.cap_slots;
+    L.off_cnt = L.off_dtab + 16 * (size_t)sched_slots;
+    L.off_fix = align_up(L.off_cnt + 4 * (size_t)(L.max_parts / 2 + 1), 256);
+    L.zero_end = L.off_fix;  // header, tables and counters are cleared per call; the list is bounded by its counter
+    L.off_chol = align_up(L.off_fix + 4 * (size_t)(rows + 1), 256);
+    L.off_mw = L.off_chol + whiten_scratch_bytes(f);
+    L.off_mu = L.off_mw + FP * FP * sizeof(float);
+    L.off_yt = L.off_mu + FP * FP * sizeof(float);
+    L.off_xp = align_up(L.off_yt + (size_t)cols * FP * sizeof(float), 256);
+    L.off_simt = align_up(L.off_xp + (size_t)rows * FP * sizeof(float), 256);
+    L.off_parts = align_up(L.off_simt + simt_half_step_workspace_bytes(f), 256);
     L.total = L.off_parts + (size_t)L.max_parts * PART_FLOATS * sizeof(float);
     return L;
 }
-size_t tc_half_step_workspace_bytes(int64_t rows, int f, int, int64_t segments) {
-    const size_t a = simt_half_step_workspace_bytes(f);
+size_t tc_half_step_workspace_bytes(int64_t rows, int64_t cols, int f, int, int64_t segments) {
     if (segments < 0) segments = rows >= 1024 ? DEFAULT_PARTS : 128;
-    const size_t b = tc_layout(2 * rows + 4096 + 1024, segments + 2).total;
-    return a > b ? a : b;
+    if (f > F) segments = 0;  // only the 128-wide primal kernel splits rows
+    return tc_layout(2 * rows + 4096 + 1024, rows, cols, f, segments + 2).total;
 }
 
 int wmf_tc_split_length() { return split_len(); }
@@ -951,50 +850,83 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     int grid = sms;
     if ((int64_t)grid > in.sched_len) grid = (int)in.sched_len;
     const int64_t extra_slot0 = (in.sched_len + grid - 1) / grid * grid;
-    const size_t need = tc_layout(extra_slot0, 0).total;
-    if (ws == nullptr || ws_bytes < need || ws_bytes < simt_half_step_workspace_bytes(in.f)) {
-        set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu (schedule of %lld slots)", ws_bytes, need,
-                  (long long)in.sched_len);
+    const int FP = tc_fp(in.f);
+    const size_t need = tc_layout(extra_slot0, in.rows, in.cols, in.f, 0).total;
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("wmf_als_half_step(tcgen05): workspace %zu < %zu (schedule of %lld slots, %lld x %lld, f = %d)", ws_bytes,
+                  need, (long long)in.sched_len, (long long)in.rows, (long long)in.cols, in.f);
         return WMF_ERR_WORKSPACE;
     }
-    // whatever is left after the tables is scratch for the segments of split rows (each needs 34 bytes of tables too)
-    int64_t max_parts = (int64_t)((ws_bytes - need - 512) / (PART_FLOATS * sizeof(float) + 34));
-    if (ws_bytes < need + 512) max_parts = 0;
+    // whatever is left after the fixed regions is scratch for the segments of split rows (each needs 34 bytes of tables too)
+    int64_t max_parts = in.f <= F ? (int64_t)((ws_bytes - need) / (PART_FLOATS * sizeof(float) + 34 + 8)) - 4 : 0;
+    if (max_parts < 2) max_parts = 0;
     if (max_parts > (1ll << 24)) max_parts = 1ll << 24;
-    const TcLayout L = tc_layout(extra_slot0, max_parts);
+    const TcLayout L = tc_layout(extra_slot0, in.rows, in.cols, in.f, max_parts);
+    if (L.total > ws_bytes) { set_error("wmf_als_half_step(tcgen05): internal workspace layout error"); return WMF_ERR_WORKSPACE; }
     max_parts = L.max_parts;
     char* base = reinterpret_cast<char*>(ws);
-    int* flags = reinterpret_cast<int*>(base) + 1;  // [0] = SIMT row counter, [1] = redo flags
-    float* hdr = reinterpret_cast<float*>(base);
     uint32_t* hdr_u = reinterpret_cast<uint32_t*>(base);
+    int* flags = reinterpret_cast<int*>(base) + 1;
     int4* tab = reinterpret_cast<int4*>(base + L.off_tab);
     int4* segtab = reinterpret_cast<int4*>(base + L.off_seg);
+    int4* dtab = reinterpret_cast<int4*>(base + L.off_dtab);
     int* counters = reinterpret_cast<int*>(base + L.off_cnt);
+    float* Mw = reinterpret_cast<float*>(base + L.off_mw);
+    float* Mu = reinterpret_cast<float*>(base + L.off_mu);
+    float* Yt = reinterpret_cast<float*>(base + L.off_yt);
+    float* Xp = reinterpret_cast<float*>(base + L.off_xp);
     float* parts = reinterpret_cast<float*>(base + L.off_parts);
-    WMF_CUDA(cudaMemsetAsync(ws, 0, L.off_parts, st));  // header, empty tables, counters
-    static bool attr_set = false;
-    if (!attr_set) {
-        WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    WMF_CUDA(cudaMemsetAsync(ws, 0, L.zero_end, st));                       // header, empty tables, counters
+    WMF_CUDA(cudaMemsetAsync(base + L.off_simt, 0, 256, st));               // the CUDA-core kernel's row counter
+    // ---- whiten: L = chol(G), Y~ = Y L^-T (zero padded to FP columns), running max of y~^2 -> hdr[2]
+    int rc = chol_whiten(in.G, in.f, FP, base + L.off_chol, Mw, Mu, flags, st);
+    if (rc) return rc;
+    rc = right_multiply(in.Y, in.cols, in.ldy, in.f, in.bias, Mw, FP, Yt, FP, FP, hdr_u + 2, st);
+    if (rc) return rc;
     HalfStepParams p = in;
-    p.KC = getenv("WMF_TC_DEBUG") ? atoi(getenv("WMF_TC_DEBUG")) : 0;  // debug: 1 = output the rhs, 2+c = output column c of A
-    p.prof = getenv("WMF_TC_PROFILE") ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
-    tc_maxima_kernel<<<1, 32, 0, st>>>(p, hdr);
-    WMF_LAUNCH_CHECK("tc_maxima_kernel");
-    tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, segtab, hdr_u, extra_slot0,
-                                                                            (int)max_parts, (int)max_parts, split_len());
+    p.Yraw = in.Y; p.ldraw = in.ldy;
+    p.Y = Yt; p.ldy = FP;
+    p.X = Xp; p.ldx = FP;
+    p.FP = FP;
+    p.f8 = (in.f + 7) / 8 * 8;
+    p.f16 = (in.f + 15) / 16 * 16;
+    p.fix_list = reinterpret_cast<int*>(base + L.off_fix);
+    p.fix_count = reinterpret_cast<int*>(hdr_u + 8);
+    p.nd_max = dual_enabled() ? tc_dual_max_entries() : 0;
+    p.prof = profile_enabled() ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
+    const int primal_ok = in.f <= F ? 1 : 0;
+    tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, segtab, dtab, hdr_u, extra_slot0,
+                                                                            (int)max_parts, (int)max_parts, split_len(),
+                                                                            primal_ok);
     WMF_LAUNCH_CHECK("tc_prep_rows_kernel");
     tc_finish_prep_kernel<<<1, 1, 0, st>>>(hdr_u, extra_slot0, (int)max_parts);
     WMF_LAUNCH_CHECK("tc_finish_prep_kernel");
-    if (p.prof) als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
-    else als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
-    WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
-    // fix-up: runs the FP32/LU kernel over the whole half-step only if a flag was raised
+    if (p.nd_max > 0) {
+        rc = tc_dual_launch(p, dtab, extra_slot0, grid, st);
+        if (rc) return rc;
+    }
+    if (primal_ok) {
+        // the attribute is per device: set it on every call (a process may drive several GPUs)
+        if (p.prof) {
+#ifdef WMF_TC_PROFILE_BUILD
+            WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
+#endif
+        } else {
+            WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
+        }
+        WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
+    }
+    // ---- unwhiten: X = X' L^-1 (all rows; fix-up rows get zeros here and their solution below)
+    rc = right_multiply(Xp, in.rows, FP, in.f, 0, Mu, FP, in.X, in.ldx, in.f, nullptr, st);
+    if (rc) return rc;
+    // ---- fix-up: the CUDA-core LU kernel solves the listed rows in the original (unwhitened) variables
     HalfStepParams fix = in;
-    fix.run_if = flags;
-    return simt_half_step(fix, ws, ws_bytes, st);
+    fix.row_order = p.fix_list;
+    fix.sched_len = in.rows;
+    fix.sched_len_dev = p.fix_count;
+    return simt_half_step(fix, base + L.off_simt, simt_half_step_workspace_bytes(in.f), st);
 }
 
 }  // namespace wmf

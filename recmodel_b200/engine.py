@@ -13,8 +13,28 @@ from . import _lib
 _workspaces = {}
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    """Raw handle of torch's current stream ON THE DEVICE OF THE OPERANDS (not of the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on(device):
+    """Context that makes ``device`` current: the C library launches on the current device, so every entry
+    point below runs under the device of its operands (WMF(device='cuda:1') with cuda:0 current)."""
+    return torch.cuda.device(device)
+
+
+def _device_of(argpos):
+    """Decorator: run the wrapped entry point with the device of its ``argpos``-th tensor argument current."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            with torch.cuda.device(args[argpos].device):
+                return fn(*args, **kwargs)
+        return wrapped
+    return deco
 
 
 def _ptr(t):
@@ -288,21 +308,25 @@ def preprocess_(data, mode, alpha, beta):
     codes = {"log": _lib.PREPROCESS_LOG, "linear": _lib.PREPROCESS_LINEAR}
     if mode not in codes:
         raise ValueError(f"Pre_process_count {mode} is not implement please use log or linear.")
-    _lib.check(lib.wmf_preprocess(_ptr(_f32(data)), data.numel(), codes[mode], float(alpha), float(beta), _stream()),
-               "wmf_preprocess")
+    with _on(data.device):
+        _lib.check(lib.wmf_preprocess(_ptr(_f32(data)), data.numel(), codes[mode], float(alpha), float(beta),
+                                      _stream(data.device)), "wmf_preprocess")
     return data
 
 
-def gram(Y, lam, ones_col0=False):
-    """G = Y^T Y + lam I (wmf_model.py:215 / :332 with the ones column)."""
+def gram(Y, lam, ones_col0=False, ws=None, out=None):
+    """G = Y^T Y + lam I (wmf_model.py:215 / :332 with the ones column). ``ws``: caller-owned scratch
+    (captured CUDA graphs must not use the shared grow-only cache)."""
     lib = _lib.load()
     _f32(Y)
     n, f = Y.shape
-    G = torch.empty((f, f), dtype=torch.float32, device=Y.device)
+    G = out if out is not None else torch.empty((f, f), dtype=torch.float32, device=Y.device)
     need = lib.wmf_gram_workspace_bytes(n, f)
-    ws = workspace(need, Y.device)
-    _lib.check(lib.wmf_gram(_ptr(Y), n, f, Y.stride(0), float(lam), int(bool(ones_col0)), _ptr(G), _ptr(ws),
-                            ws.numel(), _stream()), "wmf_gram")
+    if ws is None:
+        ws = workspace(need, Y.device)
+    with _on(Y.device):
+        _lib.check(lib.wmf_gram(_ptr(Y), n, f, Y.stride(0), float(lam), int(bool(ones_col0)), _ptr(G), _ptr(ws),
+                                ws.numel(), _stream(Y.device)), "wmf_gram")
     return G
 
 
@@ -320,8 +344,10 @@ def gram_partials(Y_local, row0, n_total, ones_col0=False):
     nloc, f = Y_local.shape
     blocks = int(lib.wmf_gram_blocks(int(n_total)))
     buf = torch.zeros((blocks, f, f), dtype=torch.float64, device=Y_local.device)
-    _lib.check(lib.wmf_gram_partials(_ptr(Y_local), int(row0), nloc, int(n_total), f, Y_local.stride(0),
-                                     int(bool(ones_col0)), _ptr(buf), buf.numel() * 8, _stream()), "wmf_gram_partials")
+    with _on(Y_local.device):
+        _lib.check(lib.wmf_gram_partials(_ptr(Y_local), int(row0), nloc, int(n_total), f, Y_local.stride(0),
+                                         int(bool(ones_col0)), _ptr(buf), buf.numel() * 8, _stream(Y_local.device)),
+                   "wmf_gram_partials")
     return buf
 
 
@@ -330,13 +356,22 @@ def gram_from_partials(partials, n_total, lam):
     lib = _lib.load()
     f = partials.shape[1]
     G = torch.empty((f, f), dtype=torch.float32, device=partials.device)
-    _lib.check(lib.wmf_gram_reduce(_ptr(partials), int(n_total), f, float(lam), _ptr(G), _stream()), "wmf_gram_reduce")
+    with _on(partials.device):
+        _lib.check(lib.wmf_gram_reduce(_ptr(partials), int(n_total), f, float(lam), _ptr(G), _stream(partials.device)),
+                   "wmf_gram_reduce")
     return G
 
 
-def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_order=True):
+def half_step_workspace_bytes(csr, f, algo=_lib.ALGO_AUTO):
+    """Scratch bytes one ``half_step`` over ``csr`` needs (its long rows included)."""
+    return int(_lib.load().wmf_als_half_step_workspace_bytes_split(csr.shape[0], csr.shape[1], f, int(algo),
+                                                                   csr.split_segments))
+
+
+def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_order=True, ws=None):
     """X = one ALS half-step over the rows of ``csr`` against fixed factors Y
-    (wmf_model.py:213-240 / :311-351)."""
+    (wmf_model.py:213-240 / :311-351). ``ws``: caller-owned scratch of ``half_step_workspace_bytes`` bytes
+    (a captured CUDA graph must own its scratch); by default the shared grow-only cache of the device."""
     lib = _lib.load()
     _f32(Y)
     _f32(G)
@@ -345,15 +380,33 @@ def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_orde
     if csr.shape[1] != Y.shape[0]:
         raise ValueError(f"count matrix has {csr.shape[1]} columns but Y has {Y.shape[0]} rows")
     X = out if out is not None else torch.empty((rows, f), dtype=torch.float32, device=Y.device)
-    need = lib.wmf_als_half_step_workspace_bytes_split(rows, f, algo, csr.split_segments)
-    ws = workspace(need, Y.device)
+    if ws is None:
+        ws = workspace(half_step_workspace_bytes(csr, f, algo), Y.device)
     order = csr.row_order if use_row_order else None
-    _lib.check(lib.wmf_als_half_step(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), rows, _ptr(order),
-                                     0 if order is None else order.numel(), _ptr(Y), Y.stride(0), f, _ptr(G), int(bool(bias)), _ptr(X), X.stride(0), int(algo),
-                                     _ptr(ws), ws.numel(), _stream()), "wmf_als_half_step")
+    with _on(Y.device):
+        _lib.check(lib.wmf_als_half_step(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), rows, csr.shape[1],
+                                         _ptr(order), 0 if order is None else order.numel(), _ptr(Y), Y.stride(0), f,
+                                         _ptr(G), int(bool(bias)), _ptr(X), X.stride(0), int(algo), _ptr(ws), ws.numel(),
+                                         _stream(Y.device)), "wmf_als_half_step")
+    half_step.last_ws = ws
     return X
 
 
+def half_step_status(ws=None):
+    """(flags, fix-up rows) of the last tcgen05 half-step that used ``ws`` (synchronises its stream)."""
+    import ctypes
+    lib = _lib.load()
+    ws = ws if ws is not None else getattr(half_step, "last_ws", None)
+    if ws is None:
+        return 0, 0
+    flags, fixed = ctypes.c_int(0), ctypes.c_int(0)
+    with _on(ws.device):
+        _lib.check(lib.wmf_als_half_step_status(_ptr(ws), ctypes.addressof(flags), ctypes.addressof(fixed),
+                                                _stream(ws.device)), "wmf_als_half_step_status")
+    return flags.value, fixed.value
+
+
+@_device_of(1)
 def sddmm_loss(csr, U, V, bias=False):
     """Device tensor [sum sq err, sum abs err, count] (float64) over the non-zero stored entries
     of ``csr`` (base_model.py:163-176 with predict, wmf_model.py:205-211)."""
@@ -369,6 +422,7 @@ def sddmm_loss(csr, U, V, bias=False):
     return out
 
 
+@_device_of(2)
 def predict_pairs(users, items, U, V, bias=False):
     """float32 scores of (users[k], items[k]); a single user broadcasts (wmf_model.py:191-211)."""
     lib = _lib.load()
@@ -386,6 +440,7 @@ def predict_pairs(users, items, U, V, bias=False):
     return out
 
 
+@_device_of(0)
 def rank_ahead(S, cand, slot, pair_user, pair_item, pair_score):
     """int32 [pairs]: how many candidates of its user's list WMF.rank puts ahead of each held-out item
     (include/wmf_b200.h: wmf_rank_ahead; base_model.py:84-95)."""
@@ -401,6 +456,7 @@ def rank_ahead(S, cand, slot, pair_user, pair_item, pair_score):
     return out
 
 
+@_device_of(2)
 def score_topk(users, cand, U, V, topn, bias=False, want_scores=False):
     """Top-``topn`` candidate ids [nu x topn] (int64), best first, for each user in ``users``
     over the shared candidate list ``cand`` (None = all items) (wmf_model.py:25-47)."""
@@ -419,6 +475,7 @@ def score_topk(users, cand, U, V, topn, bias=False, want_scores=False):
     return (ids, scores) if want_scores else ids
 
 
+@_device_of(1)
 def unweighted_half_step(csr, Y, lam):
     """X = R (inv(Y^T Y + lam I) Y^T)^T  (wmf_model.py:85 / :88)."""
     lib = _lib.load()

@@ -30,12 +30,19 @@ class ResidentEpoch:
         self.users = torch.zeros((n_users, f), dtype=torch.float32, device=dev)
         self.G_items = engine.gram(self.items, self.gamma, ones_col0=self.bias)
         self.G_users = torch.zeros_like(self.G_items)
+        self.ws = None
         if self.world == 1:   # the new factors ARE the full matrices: the half-steps write them in place
             self.X_users, self.X_items = self.users, self.items
         else:                 # this rank's new shards
             self.X_users = torch.empty((C.shape[0], f), dtype=torch.float32, device=dev)
             self.X_items = torch.empty((CT.shape[0], f), dtype=torch.float32, device=dev)
         C.row_order, CT.row_order, C.split_segments, CT.split_segments  # noqa: B018  (host-side setup, once)
+        # The captured graphs hold raw pointers into their scratch: this object owns it (sized once, kept alive
+        # with the graphs) instead of borrowing the process-wide grow-only cache of engine.workspace().
+        lib = _lib.load()
+        need = max(engine.half_step_workspace_bytes(C, f, algo), engine.half_step_workspace_bytes(CT, f, algo),
+                   int(lib.wmf_gram_workspace_bytes(max(n_users, n_items), f)))
+        self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
         self.stages = [self._user_half_step, self._user_exchange, self._item_half_step, self._item_exchange]
         self.graphs = None
         if graphs:
@@ -43,24 +50,24 @@ class ResidentEpoch:
 
     # ---- the four stages (eager form; captured verbatim)
     def _user_half_step(self):
-        engine.half_step(self.C, self.items, self.G_items, bias=self.bias, algo=self.algo, out=self.X_users)
+        engine.half_step(self.C, self.items, self.G_items, bias=self.bias, algo=self.algo, out=self.X_users, ws=self.ws)
 
     def _user_exchange(self):
         if self.world > 1:
             self.G_users.copy_(sharding.sharded_gram(self.X_users, self.ub, self.gamma, ones_col0=self.bias))
             sharding.all_gather_rows(self.X_users, self.ub, out=self.users)
         else:
-            self.G_users.copy_(engine.gram(self.users, self.gamma, ones_col0=self.bias))
+            engine.gram(self.users, self.gamma, ones_col0=self.bias, ws=self.ws, out=self.G_users)
 
     def _item_half_step(self):
-        engine.half_step(self.CT, self.users, self.G_users, bias=self.bias, algo=self.algo, out=self.X_items)
+        engine.half_step(self.CT, self.users, self.G_users, bias=self.bias, algo=self.algo, out=self.X_items, ws=self.ws)
 
     def _item_exchange(self):
         if self.world > 1:
             self.G_items.copy_(sharding.sharded_gram(self.X_items, self.ib, self.gamma, ones_col0=self.bias))
             sharding.all_gather_rows(self.X_items, self.ib, out=self.items)
         else:
-            self.G_items.copy_(engine.gram(self.items, self.gamma, ones_col0=self.bias))
+            engine.gram(self.items, self.gamma, ones_col0=self.bias, ws=self.ws, out=self.G_items)
 
     def _capture(self):
         side = torch.cuda.Stream()

@@ -125,9 +125,12 @@ class WMF(RecModel):
             items = np.array(items)
         return self.rank_batch(items, np.asarray([users], dtype=np.int64), topn)[0]
 
-    def rank_batch(self, items, users, topn):
+    def rank_batch(self, items, users, topn, distributed=False):
         """[len(users) x topn] ranked candidate ids for many users over one shared candidate list
-        in a single device pass (the batched form of ``rank``)."""
+        in a single device pass (the batched form of ``rank``). Like the reference's ``rank`` this is a LOCAL
+        call by default, also under ``torch.distributed``. ``distributed=True`` is a COLLECTIVE: every rank of
+        the default group must call it with the same arguments; each scores an equal slice of the users and the
+        id lists are all-gathered (users are independent, item factors replicated)."""
         items = np.asarray(items)
         ni = len(items)
         k = int(min(topn, ni))
@@ -137,9 +140,7 @@ class WMF(RecModel):
         cand_d = torch.from_numpy(np.ascontiguousarray(items, dtype=np.int64)).to(self.device)
         U, V = self.users_device, self.items_device
         rank_id, world = sharding.dist_info()
-        if world > 1 and k <= _lib.TOPK_MAX and len(users) >= 1024 * world:
-            # users are independent and the item factors replicated, so every rank scores an equal
-            # slice of the users and the id lists are all-gathered (the only collective of the scoring path)
+        if distributed and world > 1 and k <= _lib.TOPK_MAX:
             per = -(-len(users) // world)
             mine = users_d[rank_id * per:(rank_id + 1) * per]
             local = torch.zeros((per, k), dtype=torch.int64, device=self.device)

@@ -18,7 +18,7 @@ for dim, bias in ((128, False), (32, True)):
     mse = float(m.eval_prec(te))
     # user-sharded ranking: every rank scores a slice of the users, the id lists are all-gathered
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    top = m.rank_batch(np.arange(6000), np.arange(20000), 50)
+    top = m.rank_batch(np.arange(6000), np.arange(20000), 50, distributed=True)  # collective
     torch.cuda.synchronize(); t_rank = time.perf_counter() - t0
     res[(dim, bias)] = (m.users.copy(), m.items.copy(), mse, it, top, t_rank)
 dist.barrier()

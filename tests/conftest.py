@@ -16,6 +16,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# ---- parity ledger: every half-step comparison of the GPU run is recorded and written to
+# gpurun_out/r02_parity.json at session end (copied to profiles/ from the B200 run)
+PARITY_LEDGER = []
+
+
+def ledger_add(case, algo, **fields):
+    rec = {"case": case, "algo": algo}
+    rec.update({k: (float(v) if v is not None else None) for k, v in fields.items()})
+    PARITY_LEDGER.append(rec)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not PARITY_LEDGER:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, os.environ.get("WMF_LEDGER_NAME", "r02_parity.json")), "w") as fh:
+        json.dump({"bar": 1e-4, "measure": "max over rows of ||x - ref|| / ||ref||", "records": PARITY_LEDGER}, fh, indent=1)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     return {k: z[k] for k in z.files}

@@ -40,9 +40,14 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.wmf_preprocess(None, 10, 7, 1.0, 1.0, None) == 1
     assert "mode" in _lib.last_error()
     assert lib.wmf_gram(None, 10, 0, 0, 0.1, 0, None, None, 0, None) == 1
-    assert lib.wmf_als_half_step(None, None, None, 5, None, 0, None, 4, 100000, None, 0, None, 4, 0, None, 0, None) == 1
+    assert lib.wmf_als_half_step(None, None, None, 5, 7, None, 0, None, 4, 100000, None, 0, None, 4, 0, None, 0, None) == 1
     assert lib.wmf_gram_workspace_bytes(1000, 64) > 0
-    assert lib.wmf_als_half_step_workspace_bytes(1000, 256, 0) > 0
+    assert lib.wmf_als_half_step_workspace_bytes(1000, 500, 256, 0) > 0
+    # the tcgen05 pipeline takes every width up to 256, with or without biases (whitened factors, dual + primal kernels)
+    for f, bias in ((64, 0), (65, 1), (128, 0), (129, 1), (256, 0)):
+        assert lib.wmf_als_half_step_supports(_lib.ALGO_TCGEN05, f, bias) == 1
+    assert lib.wmf_als_half_step_supports(_lib.ALGO_TCGEN05, 257, 1) == 0
+    assert 16 <= lib.wmf_als_dual_max_entries() <= 128
     assert lib.wmf_sddmm_loss_workspace_bytes(10**6) >= 3 * 8
 
 

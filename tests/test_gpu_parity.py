@@ -9,7 +9,7 @@ import pytest
 import scipy.sparse
 import torch
 
-from conftest import WEIGHTED_CASES, csr_from, load_golden, row_rel_err
+from conftest import WEIGHTED_CASES, csr_from, ledger_add, load_golden, row_rel_err
 from oracle import wmf_oracle as orc
 from recmodel_b200 import WMF, _lib, engine
 from recmodel_b200.engine import DeviceCSR
@@ -36,6 +36,26 @@ def half_step_tol(Y, C, ref32, bias):
     x64 = step(Y, C, 0.1, np.float64)
     noise = row_rel_err(ref32, x64)
     return x64, max(HALF_STEP_TOL, 2.0 * noise)
+
+
+def check_half_step(case, algo_name, X, ref32, x64, steady=False):
+    """Record (error vs the fp32 reference, error vs the fp64 restatement, the reference's own fp32 noise, the
+    tolerance used) in the parity ledger and apply the bar. The tcgen05 path (the product) is gated at PLAIN 1e-4
+    against fp64; against the fp32 reference the bar is 1e-4 unless the reference itself is further than that from
+    fp64 on this input (first half-steps from the all-positive initialisation), where 1.5 x its noise applies.
+    The CUDA-core cross-check kernel solves the unwhitened system like the reference and shares its conditioning:
+    max(1e-4, 2 x noise)."""
+    noise = row_rel_err(ref32, x64)
+    err32, err64 = row_rel_err(X, ref32), row_rel_err(X, x64)
+    if algo_name == "tcgen05":
+        tol64, tol32 = HALF_STEP_TOL, max(HALF_STEP_TOL, 1.5 * noise)
+    else:
+        tol64 = tol32 = HALF_STEP_TOL if steady else max(HALF_STEP_TOL, 2.0 * noise)
+    ledger_add(case, algo_name, err_vs_ref32=err32, err_vs_fp64=err64, ref_noise=noise, tol_vs_fp64=tol64, tol_vs_ref32=tol32)
+    print(f"{case} [{algo_name}]: vs fp64 {err64:.2e} (tol {tol64:.1e}), vs ref32 {err32:.2e} (tol {tol32:.1e}), ref noise {noise:.2e}")
+    assert err64 < tol64, (case, algo_name, err64, tol64)
+    assert err32 < tol32, (case, algo_name, err32, tol32)
+    return err64
 
 
 def run_half_step(Y, C, bias, algo, cuda_device, use_row_order=True):
@@ -118,13 +138,12 @@ def test_half_step_vs_reference_golden(cuda_device, name, dim, bias, mode, algo_
     C = csr_from(g, "train")
     C.data = orc.preprocess_counts(C.data, mode, 10, 1)
     CT = C.T.tocsr()
-    x64, tol = half_step_tol(g["items0"], C, g["users_half1"], bias)
+    step = orc.half_step_bias if bias else orc.half_step
     X, _ = run_half_step(g["items0"], C, bias, algo, cuda_device)
-    assert row_rel_err(X, g["users_half1"]) < tol
-    assert row_rel_err(X, x64) < tol
-    x64, tol = half_step_tol(g["users_half1"], CT, g["items_half1"], bias)
+    check_half_step(f"golden/{name}/users_half1", algo_name, X, g["users_half1"], step(g["items0"], C, 0.1, np.float64))
     Xi, _ = run_half_step(g["users_half1"], CT, bias, algo, cuda_device)
-    assert row_rel_err(Xi, g["items_half1"]) < tol
+    check_half_step(f"golden/{name}/items_half1", algo_name, Xi, g["items_half1"],
+                    step(g["users_half1"], CT, 0.1, np.float64))
 
 
 @pytest.mark.parametrize("algo_name,algo", ALGOS)
@@ -149,19 +168,15 @@ def test_half_step_vs_oracle_realistic(cuda_device, users, items, nnz, dim, bias
     # within the same distance of the fp32 reference.
     rows = slice(0, min(users, 1500))
     ref_u = step(Y, C[rows], 0.1)
-    x64, tol = half_step_tol(Y, C[rows], ref_u, bias)
     X, _ = run_half_step(Y, C, bias, algo, cuda_device)
-    err64, err32 = row_rel_err(X[rows], x64), row_rel_err(X[rows], ref_u)
-    print(f"first half-step: gpu-vs-fp64 {err64:.2e}, gpu-vs-ref32 {err32:.2e}, ref32-vs-fp64 tol {tol:.2e}")
-    assert err64 < tol and err32 < tol
+    case = f"realistic/{users}x{items}/f{f}{'b' if bias else ''}"
+    check_half_step(case + "/first_user_half_step", algo_name, X[rows], ref_u, step(Y, C[rows], 0.1, np.float64))
     # second half-step from mixed-sign factors (the steady-state regime): plain 1e-4
     full_u = X if users <= 1500 else step(Y, C, 0.1)
     sel = slice(0, min(items, 800))
     ref_i = step(full_u, CT[sel], 0.1)
     Xi, _ = run_half_step(full_u, CT[sel], bias, algo, cuda_device)
-    err = row_rel_err(Xi, ref_i)
-    print(f"second half-step: gpu-vs-ref32 {err:.2e}")
-    assert err < HALF_STEP_TOL
+    check_half_step(case + "/item_half_step", algo_name, Xi, ref_i, step(full_u, CT[sel], 0.1, np.float64), steady=True)
 
 
 @pytest.mark.parametrize("algo_name,algo", ALGOS)
@@ -185,10 +200,9 @@ def test_half_step_edge_rows(cuda_device, f, bias, algo_name, algo):
         Y[:, 0] = rng.random(N).astype(np.float32)
     step = orc.half_step_bias if bias else orc.half_step
     ref = step(Y, C, 0.1)
-    x64, tol = half_step_tol(Y, C, ref, bias)
     X, _ = run_half_step(Y, C, bias, algo, cuda_device)
     assert np.all(X[np.array(lens) == 0] == 0)
-    assert row_rel_err(X, x64) < tol
+    check_half_step(f"edge_rows/f{f}{'b' if bias else ''}", algo_name, X, ref, step(Y, C, 0.1, np.float64))
     X2, _ = run_half_step(Y, C, bias, algo, cuda_device, use_row_order=False)
     np.testing.assert_array_equal(X, X2)  # processing order never changes a row's arithmetic
 
@@ -207,7 +221,13 @@ def test_half_step_indefinite_falls_back_to_lu(cuda_device, algo_name, algo):
     x64, tol = half_step_tol(Y, C, ref, False)
     X, _ = run_half_step(Y, C, False, algo, cuda_device)
     assert np.all(np.isfinite(X))
-    assert row_rel_err(X, x64) < max(tol, 1e-3)  # indefinite systems: conditioning-limited
+    err = row_rel_err(X, x64)
+    ledger_add("indefinite_negative_weights/f64", algo_name, err_vs_ref32=row_rel_err(X, ref), err_vs_fp64=err,
+               ref_noise=row_rel_err(ref, x64), tol_vs_fp64=max(tol, 1e-3), tol_vs_ref32=None)
+    assert err < max(tol, 1e-3)  # indefinite systems: conditioning-limited (LU kernel on both paths)
+    if algo == _lib.ALGO_TCGEN05:  # every row with entries went through the per-row fix-up list, none through a redo
+        flags, fixed = engine.half_step_status()
+        assert fixed == int((np.diff(C.indptr) > 0).sum()) and (flags & 2) == 0
 
 
 def test_half_step_split_rows(cuda_device):
@@ -231,10 +251,7 @@ def test_half_step_split_rows(cuda_device):
     assert np.all(np.isfinite(X))
     check = np.array([3, 40, 41, 700, 1199, 0, 1, 2, 500])
     ref = orc.half_step(Y, C[check], 0.1)
-    x64, tol = half_step_tol(Y, C[check], ref, False)
-    err = row_rel_err(X[check], x64)
-    print(f"split rows: gpu-vs-fp64 {err:.2e} (tol {tol:.2e})")
-    assert err < tol
+    check_half_step("split_rows/f128", "tcgen05", X[check], ref, orc.half_step(Y, C[check], 0.1, np.float64))
     Xs, _ = run_half_step(Y, C, False, _lib.ALGO_SIMT, cuda_device)
     assert row_rel_err(X, Xs) < HALF_STEP_TOL
     X2, _ = run_half_step(Y, C, False, _lib.ALGO_TCGEN05, cuda_device, use_row_order=False)
@@ -278,7 +295,9 @@ def test_half_step_full_size_properties(cuda_device):
         worst_noise = max(worst_noise, noise)
         worst = max(worst, np.linalg.norm(X[r] - x) / np.linalg.norm(x))
     print(f"full size: worst gpu-vs-fp64 {worst:.2e}; reference fp32-vs-fp64 on the same rows {worst_noise:.2e}")
-    assert worst < max(HALF_STEP_TOL, 2 * worst_noise)
+    ledger_add("cfg2_full/first_user_half_step(49 rows)", "tcgen05", err_vs_ref32=None, err_vs_fp64=worst,
+               ref_noise=worst_noise, tol_vs_fp64=HALF_STEP_TOL, tol_vs_ref32=None)
+    assert worst < HALF_STEP_TOL
     X2 = engine.half_step(Cd, Yd, G).cpu().numpy()
     np.testing.assert_array_equal(X, X2)
     half = users // 2
@@ -303,6 +322,8 @@ def test_half_step_full_size_properties(cuda_device):
         x = np.linalg.solve(Gi64 + (Yr * d[:, None]).T @ Yr, (d + 1) @ Yr)
         worst_i = max(worst_i, np.linalg.norm(Xi[r] - x) / np.linalg.norm(x))
     print(f"full size, item side: worst gpu-vs-fp64 over rows of {lens[order[0]]} .. {lens[order[5001]]} entries {worst_i:.2e}")
+    ledger_add("cfg2_full/item_half_step(heaviest rows)", "tcgen05", err_vs_ref32=None, err_vs_fp64=worst_i,
+               ref_noise=None, tol_vs_fp64=HALF_STEP_TOL / 2, tol_vs_ref32=None)
     assert worst_i < HALF_STEP_TOL / 2
     Xib = engine.half_step(CTd.row_slice(0, items // 3), Xd, Gi).cpu().numpy()
     np.testing.assert_array_equal(Xib, Xi[:items // 3])
@@ -505,8 +526,8 @@ def test_recompute_factors_methods(cuda_device):
     m = WMF(num_items=C.shape[1], num_users=C.shape[0], dim=8, gamma=0.1, weighted=True, bias=True)
     Y = g["items0"].copy()
     X = m.recompute_factors_bias(Y, C, 0.1, cores=1)
-    _, tol = half_step_tol(g["items0"], C, g["users_half1"], True)
-    assert row_rel_err(X, g["users_half1"]) < tol
+    check_half_step("recompute_factors_bias/f9", "tcgen05", X, g["users_half1"],
+                    orc.half_step_bias(g["items0"], C, 0.1, np.float64))
     assert np.all(Y[:, 0] == 1)  # the reference overwrites the caller's bias column (wmf_model.py:331)
     g2 = load_golden("weighted_nobias_f16")
     C2 = csr_from(g2, "train")
@@ -591,3 +612,40 @@ def test_recall_quality_planted_structure(cuda_device):
                         random_state=3)["Recall@20"]
     assert ref > 0.3
     assert abs(float(ours) - float(ref)) <= 0.005
+
+
+# ------------------------------------------------------------------------------- K2, dual kernel / routing
+@pytest.mark.parametrize("f,bias", [(16, False), (64, False), (65, True), (128, False), (129, True), (192, False),
+                                    (256, False)])
+def test_half_step_dual_rows_every_length(cuda_device, f, bias):
+    """Rows of every length 1 .. dual_max + 8 (the routing boundary included), a few long ones, an empty one and
+    one with a stored zero weight (it must stay off the dual side, whose right-hand side divides by sqrt(d)):
+    the tcgen05 pipeline (dual kernel for short rows; primal kernel or CUDA-core kernel for the rest) against the
+    fp64 restatement at plain 1e-4, steady-state-like mixed-sign factors and the all-positive first-epoch kind."""
+    nd = int(_lib.load().wmf_als_dual_max_entries())
+    rng = np.random.default_rng(1000 + f)
+    N = 1500
+    lens = list(range(1, nd + 9)) + [0, 150, 400, 1100, 5]
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    indices = np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lens]).astype(np.int32)
+    data = orc.preprocess_counts(rng.integers(1, 6, indptr[-1]).astype(np.float32))
+    data[indptr[len(lens) - 1] + 2] = 0.0  # the 5-entry row holds a zero weight
+    C = scipy.sparse.csr_matrix((data, indices, indptr), shape=(len(lens), N))
+    step = orc.half_step_bias if bias else orc.half_step
+    for kind in ("positive", "mixed"):
+        Y = rng.random((N, f)).astype(np.float32) if kind == "positive" else (rng.standard_normal((N, f)) * 0.3).astype(np.float32)
+        if bias:
+            Y[:, 0] = (rng.random(N) * 0.5).astype(np.float32)   # beta < d: all weights stay positive
+        X, _ = run_half_step(Y, C, bias, _lib.ALGO_TCGEN05, cuda_device)
+        flags, fixed = engine.half_step_status()
+        assert np.all(X[np.array(lens) == 0] == 0) and np.all(np.isfinite(X))
+        check_half_step(f"dual_rows/f{f}{'b' if bias else ''}/{kind}", "tcgen05", X, step(Y, C, 0.1), step(Y, C, 0.1, np.float64))
+        assert (flags & 2) == 0
+        if f <= 128:                   # only a negative weight needs the CUDA-core kernel: with biases the stored
+            assert fixed == (1 if bias else 0)   # zero becomes 0 - beta < 0
+        else:                          # above 128 features the rows longer than dual_max (and the zero-weight row) do
+            assert fixed == sum(1 for n in lens if n > nd) + 1
+        X2, _ = run_half_step(Y, C, bias, _lib.ALGO_TCGEN05, cuda_device, use_row_order=False)
+        np.testing.assert_array_equal(X, X2)
+        Xa, _ = run_half_step(Y, C[:40], bias, _lib.ALGO_TCGEN05, cuda_device)   # row sharding never changes a row's bits
+        np.testing.assert_array_equal(Xa, X[:40])
