@@ -43,7 +43,7 @@ bool tc_half_step_supported(int f, int bias);
 size_t tc_half_step_workspace_bytes(int64_t rows, int64_t cols, int f, int bias, int64_t segments);  // segments < 0: default scratch
 int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream_t st);
 // dual (n x n) kernel for the rows of the dual table (half_step_dual.cu)
-int tc_dual_launch(const HalfStepParams& p, const int4* dtab, int64_t slots, int grid, cudaStream_t st);
+int tc_dual_launch(const HalfStepParams& p, const int4* dtab, const uint32_t* hdr_u, int grid, cudaStream_t st);
 int tc_dual_max_entries();
 
 }  // namespace wmf

@@ -19,6 +19,7 @@
 //
 // Roles as in the primal kernel: warps 0-15 four solver groups (one 128-column accumulator each), warps 16-23 gather,
 // warp 24 MMA issue. One persistent CTA per SM walks the slots s = k * gridDim + blockIdx of the dual table.
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "half_step.cuh"
 #include "factor8.cuh"
@@ -58,15 +59,20 @@ constexpr int NBARS = 2 * NST + 3 * NGROUP;
 constexpr int OFF_TMEM_PTR = OFF_BARS + NBARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(ND_MAX % 16 == 0 && ND_MAX <= 128, "dual rows must fit the TMEM lanes");
+static_assert(ND_MAX % 16 == 0 && ND_MAX <= 128, "dual rows must fit the TMEM lanes");  // the kernel itself takes any n <= 128
 
 __device__ __forceinline__ void sts2u(uint32_t a, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, int nslots_total, int* __restrict__ flags) {
+als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const uint32_t* __restrict__ hdr_u,
+                          int* __restrict__ flags) {
     extern __shared__ uint8_t smem_raw[];
+    // slots [slot_lo, slot_hi) hold this kernel's rows (tc_prep_rows_kernel); none: nothing to set up
+    const int slot_hi = (int)hdr_u[11];
+    if (slot_hi == 0) return;
+    const int slot_lo = (int)(0x7fffffffu - hdr_u[10]);
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = smem_base + OFF_BARS;
     auto bar_full = [&](int s) { return bars + 8u * s; };
@@ -105,11 +111,12 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, int n
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
     const int ts = (int)gridDim.x;
-    const int nslots = (nslots_total - (int)blockIdx.x + ts - 1) / ts;
+    const int k_lo = slot_lo / ts;                                    // first round of slots worth walking
+    const int nslots = (slot_hi - (int)blockIdx.x + ts - 1) / ts - k_lo;
     auto ent_at = [&](int k) -> RowEnt {
         RowEnt e{-1, 0, 0, 0, -1};
         if (k < nslots) {
-            const int slot = k * ts + (int)blockIdx.x;
+            const int slot = (k + k_lo) * ts + (int)blockIdx.x;
             e = unpack_ent(__ldg(dtab + slot), slot);
         }
         return e;
@@ -232,6 +239,7 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, int n
         const int qw = warp & 3;        // TMEM lane quarter this warp may access
         const int t = qw * 32 + lane;   // matrix row owned by this thread = TMEM lane = entry of the CSR row
         const int bar_id = 1 + g;
+        const int ISSUE_T = WMF_TC_BALANCED ? 32 * g : 0;  // thread of the group that issues its rank-8 update MMAs
         const uint32_t gs = smem_base + OFF_GROUPS + g * GROUP_BYTES;
         const uint32_t tileH = gs + G_OFF_TILEH, tileL = gs + G_OFF_TILEL;
         const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN;
@@ -278,6 +286,19 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, int n
 #pragma unroll
                 for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, rel == i ? 1.0f : 0.0f);  // I + W W^T
                 const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
+#if WMF_TC_BALANCED
+                // The 8 threads that hold the pivot rows publish them; the serial 8x8 factor is run by warp g of
+                // group g, whatever warp the pivot rows live in: the four groups' serial chains then sit on four
+                // different warp schedulers (warp id mod 4) instead of piling up on the scheduler of the quarter all
+                // groups happen to be in (short dual rows never leave quarter 0).
+                if (rel >= 0 && rel < NB) {
+                    sts4(Dblk + rel * 32, a[0], a[1], a[2], a[3]);
+                    sts4(Dblk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
+                    sts1(Dblk + 256 + rel * 4, bt);
+                }
+                named_bar(bar_id, GROUP);
+                if (qw == g) {
+#else
                 if (qw == (c0 >> 5)) {
                     // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
                     if (rel >= 0 && rel < NB) {
@@ -286,6 +307,7 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, int n
                         sts1(Dblk + 256 + rel * 4, bt);
                     }
                     __syncwarp();
+#endif
                     float d[36], bb[NB];
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
@@ -368,7 +390,7 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, int n
                     fence_async_smem();
                     tc_fence_before();
                     named_bar(bar_id, GROUP);
-                    if (t == 0) {
+                    if (t == ISSUE_T) {
                         tc_fence_after();
                         const uint32_t start = (uint32_t)((c0 + NB) >> 4) << 4;
                         const uint32_t idesc = IDESC_TF32_NEG_M128 | ((((uint32_t)n16 - start) >> 3) << 17);
@@ -448,13 +470,22 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, int n
 
 }  // namespace dual
 
-int tc_dual_max_entries() { return dual::ND_MAX; }
+// WMF_TC_DUAL_MAX=<entries> (multiple of 16, <= 128; read once) overrides the routing threshold for experiments
+int tc_dual_max_entries() {
+    static const int v = [] {
+        const char* e = getenv("WMF_TC_DUAL_MAX");
+        int x = e ? atoi(e) : dual::ND_MAX;
+        if (x < 16 || x > 128) x = dual::ND_MAX;
+        return x / 16 * 16;
+    }();
+    return v;
+}
 
-int tc_dual_launch(const HalfStepParams& p, const int4* dtab, int64_t slots, int grid, cudaStream_t st) {
+int tc_dual_launch(const HalfStepParams& p, const int4* dtab, const uint32_t* hdr_u, int grid, cudaStream_t st) {
     WMF_CUDA(cudaFuncSetAttribute(dual::als_half_step_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   dual::SMEM_BYTES));
     int* flags = reinterpret_cast<int*>(p.fix_count) - 7;   // header word 1 (fix_count is word 8)
-    dual::als_half_step_dual_kernel<<<grid, dual::THREADS, dual::SMEM_BYTES, st>>>(p, dtab, (int)slots, flags);
+    dual::als_half_step_dual_kernel<<<grid, dual::THREADS, dual::SMEM_BYTES, st>>>(p, dtab, hdr_u, flags);
     WMF_LAUNCH_CHECK("als_half_step_dual_kernel");
     return WMF_OK;
 }

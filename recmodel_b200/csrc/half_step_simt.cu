@@ -41,6 +41,9 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
     const int ntiles = T * (T + 1) / 2;
     if (p.run_if != nullptr && *p.run_if == 0) return;  // fix-up launch with nothing to fix
     const int64_t sched_len = p.sched_len_dev ? (int64_t)*p.sched_len_dev : p.sched_len;  // device-side fix-up list
+    // fix-up of the tcgen05 pipeline: Y holds the whitened factors (ones column already folded in), G the identity,
+    // the bias that shifts the weights comes from the original factors
+    const bool whitened = p.Yraw != nullptr;
 
     while (true) {
         if (tid == 0) misc[0] = atomicAdd(p.counter, 1);
@@ -72,13 +75,14 @@ __global__ __launch_bounds__(HS_THREADS) void als_half_step_simt_kernel(HalfStep
                     float d = 0.f;
                     const float* yrow = p.Y;
                     if (k < kc) {
-                        yrow = p.Y + (int64_t)p.indices[base + k] * p.ldy;
+                        const int64_t col = p.indices[base + k];
+                        yrow = p.Y + col * p.ldy;
                         d = p.data[base + k];
-                        if (p.bias) d = __fsub_rn(d, yrow[0]);  // wmf_model.py:343
+                        if (p.bias) d = __fsub_rn(d, whitened ? p.Yraw[col * p.ldraw] : yrow[0]);  // wmf_model.py:343
                     }
                     for (int c = lane; c < FP; c += 32) {
                         float y = 0.f;
-                        if (k < kc && c < f) y = (p.bias && c == 0) ? 1.0f : yrow[c];
+                        if (k < kc && c < f) y = (p.bias && c == 0 && !whitened) ? 1.0f : yrow[c];
                         Ys[k * FP + c] = y;
                         Ws[k * FP + c] = d * y;
                     }

@@ -153,12 +153,29 @@ __global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, in
         int64_t n = hi - lo;
         float m = 0.0f;
         bool neg = false, zero = false;
-        for (int64_t i = lo + lane; i < hi; i += 32) {
-            float d = __ldg(p.data + i);
-            if (p.bias) d = __fsub_rn(d, __ldg(p.Yraw + (int64_t)__ldg(p.indices + i) * p.ldraw));
-            neg |= !(d >= 0.0f);   // NaN weights go to the LU kernel too
-            zero |= d == 0.0f;
-            m = fmaxf(m, fabsf(d));
+        // eight loads in flight per lane: the longest row of the matrix is this kernel's critical path
+        for (int64_t i0 = lo + lane; i0 < hi; i0 += 32 * 8) {
+            float d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t i = i0 + 32 * u;
+                d[u] = i < hi ? __ldg(p.data + i) : 1.0f;
+            }
+            if (p.bias) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t i = i0 + 32 * u;
+                    if (i < hi) d[u] = __fsub_rn(d[u], __ldg(p.Yraw + (int64_t)__ldg(p.indices + i) * p.ldraw));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (i0 + 32 * u < hi) {
+                    neg |= !(d[u] >= 0.0f);   // NaN weights go to the LU kernel too
+                    zero |= d[u] == 0.0f;
+                    m = fmaxf(m, fabsf(d[u]));
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -179,10 +196,12 @@ __global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, in
             float4* x = reinterpret_cast<float4*>(p.X + row * p.ldx);  // whitened solution: ld = FP, 16-byte aligned
             for (int i = lane; i < p.FP / 4; i += 32) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else if (dual) {
+            if (lane == 0) { atomicMax(hdr_u + 10, 0x7fffffffu - (uint32_t)s); atomicMax(hdr_u + 11, (uint32_t)s + 1u); }
             de.y = (int32_t)n;
             de.z = (int32_t)(uint32_t)lo;
             de.w = (int32_t)((uint32_t)((lo >> 32) & 0xFFFF) | sbits);
         } else {
+            if (lane == 0) atomicMax(hdr_u + 9, (uint32_t)s + 1u);
             // equal segments of whole sub-chunks, none empty (a function of the row length alone)
             int nseg = 1;
             int64_t seg_len = n;
@@ -293,7 +312,10 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
     const int ts = (int)gridDim.x;
     const int total_slots = (int)hdr_u[4];  // schedule + extra segment slots (set by the prep kernels), < 2^31
     const int nextra = (total_slots - (int)extra_slot0 - (int)blockIdx.x + ts - 1) / ts;
-    const int nslots = nextra + ((int)extra_slot0 - (int)blockIdx.x + ts - 1) / ts;
+    // schedule slots at and beyond hdr[9] hold no row of this kernel (longest-first schedules put the short rows of
+    // the dual kernel and the empty rows last): nobody walks them
+    const int sched_end = min((int)extra_slot0, ((int)hdr_u[9] + ts - 1) / ts * ts);
+    const int nslots = nextra + (sched_end - (int)blockIdx.x + ts - 1) / ts;
     const int base_x = (int)extra_slot0 + (int)blockIdx.x, base_s = (int)blockIdx.x - nextra * ts;
     auto ent_at = [&](int k) -> RowEnt {
         RowEnt e{-1, 0, 0, 0, -1};
@@ -544,6 +566,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         const int q = warp & 3;        // TMEM lane quarter this warp may access
         const int t = q * 32 + lane;   // matrix row owned by this thread = TMEM lane
         const int bar_id = 1 + g;
+        const int ISSUE_T = WMF_TC_BALANCED ? 32 * g : 0;  // thread of the group that issues its rank-8 update MMAs
         const uint32_t gs = smem_base + OFF_GROUPS + g * GROUP_BYTES;
         const uint32_t tileH = gs + G_OFF_TILEH, tileL = gs + G_OFF_TILEL;
         const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN;
@@ -644,6 +667,19 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, rel == i ? 1.0f : 0.0f);  // I + sum d y~ y~^T
                 if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
                 const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
+#if WMF_TC_BALANCED
+                // The 8 threads that hold the pivot rows publish them; the serial 8x8 factor is run by warp g of
+                // group g, whatever warp the pivot rows live in: the four groups' serial chains then sit on four
+                // different warp schedulers (warp id mod 4) instead of piling up on the scheduler of the quarter all
+                // groups happen to be in (short dual rows never leave quarter 0).
+                if (rel >= 0 && rel < NB) {
+                    sts4(Dblk + rel * 32, a[0], a[1], a[2], a[3]);
+                    sts4(Dblk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
+                    sts1(Dblk + 256 + rel * 4, bt);
+                }
+                named_bar(bar_id, GROUP);
+                if (q == g) {
+#else
                 if (q == (c0 >> 5)) {
                     // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
                     if (rel >= 0 && rel < NB) {
@@ -652,6 +688,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                         sts1(Dblk + 256 + rel * 4, bt);
                     }
                     __syncwarp();
+#endif
                     float d[36], bb[NB];
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
@@ -740,7 +777,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                     tc_fence_before();
                     if (prof) t3 = clock64();
                     named_bar(bar_id, GROUP);
-                    if (t == 0) {
+                    if (t == ISSUE_T) {
                         // S[:, j] -= P P[j]^T for the live columns j >= c0 + 8 (all 128 rows: Gauss-Jordan)
                         tc_fence_after();
                         if (prof) { t4 = clock64(); ph_p += t4 - t3; }
@@ -804,7 +841,8 @@ bool tc_half_step_supported(int f, int bias) { return f >= 1 && f <= 256 && (!bi
 
 // Workspace (bytes from a 256-aligned base):
 //   [0, 1024)   header: [1] flags (1 unused, 2 failed pivot, 8 G not positive definite), [2] max y~^2 (float bits),
-//               [4] total slots, [5] split rows, [6] partial slots, [7] extra slots, [8] fix-up rows; [256, 768) profile
+//               [4] total slots, [5] split rows, [6] partial slots, [7] extra slots, [8] fix-up rows, [9] end of the
+//               primal rows' slots, [10] 0x7fffffff - first dual slot, [11] end of the dual rows' slots; [256, 768) profile
 //   tables      primal row table + split table (32 B per slot), dual row table (16 B per slot), split-row counters,
 //               fix-up list (4 B per row)
 //   whitening   double scratch of the Cholesky, the two FP x FP multipliers, Y~ (cols x FP), X' (rows x FP)
@@ -812,8 +850,8 @@ bool tc_half_step_supported(int f, int bias) { return f >= 1 && f <= 256 && (!bi
 //   parts       partial-Gram scratch for the segments of split rows: whatever is left
 struct TcLayout {
     int64_t cap_slots, max_parts;
-    size_t off_tab, off_seg, off_dtab, off_cnt, off_fix, zero_end, off_chol, off_mw, off_mu, off_yt, off_xp, off_simt,
-        off_parts, total;
+    size_t off_tab, off_seg, off_dtab, off_cnt, off_fix, zero_end, off_chol, off_mw, off_mu, off_eye, off_yt, off_xp,
+        off_simt, off_parts, total;
 };
 static int tc_fp(int f) { return f <= 128 ? 128 : 256; }
 static TcLayout tc_layout(int64_t sched_slots, int64_t rows, int64_t cols, int f, int64_t parts) {
@@ -830,7 +868,8 @@ static TcLayout tc_layout(int64_t sched_slots, int64_t rows, int64_t cols, int f
     L.off_chol = align_up(L.off_fix + 4 * (size_t)(rows + 1), 256);
     L.off_mw = L.off_chol + whiten_scratch_bytes(f);
     L.off_mu = L.off_mw + FP * FP * sizeof(float);
-    L.off_yt = L.off_mu + FP * FP * sizeof(float);
+    L.off_eye = L.off_mu + FP * FP * sizeof(float);           // f x f identity: the whitened G of the fix-up kernel
+    L.off_yt = L.off_eye + FP * FP * sizeof(float);
     L.off_xp = align_up(L.off_yt + (size_t)cols * FP * sizeof(float), 256);
     L.off_simt = align_up(L.off_xp + (size_t)rows * FP * sizeof(float), 256);
     L.off_parts = align_up(L.off_simt + simt_half_step_workspace_bytes(f), 256);
@@ -879,7 +918,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     WMF_CUDA(cudaMemsetAsync(ws, 0, L.zero_end, st));                       // header, empty tables, counters
     WMF_CUDA(cudaMemsetAsync(base + L.off_simt, 0, 256, st));               // the CUDA-core kernel's row counter
     // ---- whiten: L = chol(G), Y~ = Y L^-T (zero padded to FP columns), running max of y~^2 -> hdr[2]
-    int rc = chol_whiten(in.G, in.f, FP, base + L.off_chol, Mw, Mu, flags, st);
+    int rc = chol_whiten(in.G, in.f, FP, base + L.off_chol, Mw, Mu, reinterpret_cast<float*>(base + L.off_eye), flags, st);
     if (rc) return rc;
     rc = right_multiply(in.Y, in.cols, in.ldy, in.f, in.bias, Mw, FP, Yt, FP, FP, hdr_u + 2, st);
     if (rc) return rc;
@@ -902,7 +941,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     tc_finish_prep_kernel<<<1, 1, 0, st>>>(hdr_u, extra_slot0, (int)max_parts);
     WMF_LAUNCH_CHECK("tc_finish_prep_kernel");
     if (p.nd_max > 0) {
-        rc = tc_dual_launch(p, dtab, extra_slot0, grid, st);
+        rc = tc_dual_launch(p, dtab, hdr_u, grid, st);
         if (rc) return rc;
     }
     if (primal_ok) {
@@ -918,15 +957,20 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
         }
         WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
     }
-    // ---- unwhiten: X = X' L^-1 (all rows; fix-up rows get zeros here and their solution below)
-    rc = right_multiply(Xp, in.rows, FP, in.f, 0, Mu, FP, in.X, in.ldx, in.f, nullptr, st);
-    if (rc) return rc;
-    // ---- fix-up: the CUDA-core LU kernel solves the listed rows in the original (unwhitened) variables
+    // ---- fix-up: the CUDA-core LU kernel solves the listed rows, in the whitened variables as well (same
+    // conditioning as the tensor-core rows): Y~, G = I, weights shifted by the original bias column
     HalfStepParams fix = in;
+    fix.Y = Yt; fix.ldy = FP;
+    fix.Yraw = in.Y; fix.ldraw = in.ldy;
+    fix.G = reinterpret_cast<const float*>(base + L.off_eye);
+    fix.X = Xp; fix.ldx = FP;
     fix.row_order = p.fix_list;
     fix.sched_len = in.rows;
     fix.sched_len_dev = p.fix_count;
-    return simt_half_step(fix, base + L.off_simt, simt_half_step_workspace_bytes(in.f), st);
+    rc = simt_half_step(fix, base + L.off_simt, simt_half_step_workspace_bytes(in.f), st);
+    if (rc) return rc;
+    // ---- unwhiten: X = X' L^-1
+    return right_multiply(Xp, in.rows, FP, in.f, 0, Mu, FP, in.X, in.ldx, in.f, nullptr, st);
 }
 
 }  // namespace wmf

@@ -21,25 +21,22 @@ namespace wmf {
 
 namespace {
 
-constexpr int CW_THREADS = 1024;
-constexpr int CW_LPR = 8;                       // lanes that share one matrix row / column
-constexpr int CW_ROWS = CW_THREADS / CW_LPR;    // rows per pass
-
-__device__ __forceinline__ double shfl_xor_d(double v, int o) {
-    return __shfl_xor_sync(0xffffffffu, v, o);
-}
+constexpr int CW_THREADS = 256;   // one thread per matrix row / column (f <= 256)
 
 // A (double, ld) holds L in its lower triangle (diagonal included) and, after the second phase, column j of
 // L^-1 below the diagonal in ROW j of the strict upper triangle; 1 / L_jj in dinv.
+// The work is ~f^3/2 double FMAs (nothing); the cost is the chain of f dependent columns, so every phase is
+// written for latency: thread i owns row i (Cholesky, two barriers per column, four accumulators per dot product),
+// thread j owns column j of L^-1 (forward substitution, no barrier at all: it only reads L and its own column).
 __global__ void __launch_bounds__(CW_THREADS, 1)
 chol_whiten_kernel(const float* __restrict__ G, int f, int FP, double* __restrict__ gscratch, int use_smem,
-                   float* __restrict__ Mw, float* __restrict__ Mu, int* __restrict__ flags) {
+                   float* __restrict__ Mw, float* __restrict__ Mu, float* __restrict__ eye, int* __restrict__ flags) {
     extern __shared__ double cw_smem[];
-    __shared__ double s_piv;
+    __shared__ double s_rpiv;
     __shared__ int s_bad;
-    if (threadIdx.x == 0) s_bad = 0;
     const int tid = threadIdx.x;
-    const int ld = f | 1;  // odd leading dimension: column walks do not hit one bank
+    if (tid == 0) s_bad = 0;
+    const int ld = f | 1;  // odd leading dimension: row-strided accesses spread over the banks
     double* A = use_smem ? cw_smem : gscratch;
     double* dinv = A + (size_t)f * ld;
     for (int e = tid; e < f * f; e += CW_THREADS) {
@@ -47,60 +44,51 @@ chol_whiten_kernel(const float* __restrict__ G, int f, int FP, double* __restric
         if (j <= i) A[i * ld + j] = (double)G[(size_t)i * f + j];
     }
     __syncthreads();
-    const int q = tid & (CW_LPR - 1), rg = tid / CW_LPR;
-    const int passes = (f + CW_ROWS - 1) / CW_ROWS;
     // ---- left-looking Cholesky: column k from the k columns before it
+    const int i = tid;
+    const double* ai = A + (size_t)(i < f ? i : 0) * ld;
     for (int k = 0; k < f; ++k) {
-        double s[2] = {0.0, 0.0};
-#pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-            if (ps >= passes) break;
-            const int i = ps * CW_ROWS + rg;
-            double acc = 0.0;
-            if (i >= k && i < f) {
-                const double* ai = A + (size_t)i * ld;
-                const double* ak = A + (size_t)k * ld;
-                for (int j = q; j < k; j += CW_LPR) acc = fma(ai[j], ak[j], acc);
+        double s = 0.0;
+        if (i >= k && i < f) {
+            const double* ak = A + (size_t)k * ld;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int j = 0;
+            for (; j + 4 <= k; j += 4) {
+                a0 = fma(ai[j], ak[j], a0);
+                a1 = fma(ai[j + 1], ak[j + 1], a1);
+                a2 = fma(ai[j + 2], ak[j + 2], a2);
+                a3 = fma(ai[j + 3], ak[j + 3], a3);
             }
-            acc += shfl_xor_d(acc, 1);
-            acc += shfl_xor_d(acc, 2);
-            acc += shfl_xor_d(acc, 4);
-            if (i >= k && i < f) s[ps] = A[(size_t)i * ld + k] - acc;
-            if (i == k && q == 0) {
-                if (!(s[ps] > 0.0)) { s_bad = 1; s[ps] = 1.0; }  // G is not positive definite
-                s_piv = sqrt(s[ps]);
+            for (; j < k; ++j) a0 = fma(ai[j], ak[j], a0);
+            s = ai[k] - ((a0 + a1) + (a2 + a3));
+            if (i == k) {
+                if (!(s > 0.0)) { s_bad = 1; s = 1.0; }  // G is not positive definite
+                const double r = rsqrt(s);
+                s_rpiv = r;           // L_kk = s * r = sqrt(s) falls out of the common store below
+                dinv[k] = r;          // 1 / L_kk
             }
         }
         __syncthreads();
-        const double piv = s_piv;
-#pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-            if (ps >= passes) break;
-            const int i = ps * CW_ROWS + rg;
-            if (q == 0 && i >= k && i < f) A[(size_t)i * ld + k] = (i == k) ? piv : s[ps] / piv;
-        }
+        if (i >= k && i < f) A[(size_t)i * ld + k] = s * s_rpiv;
         __syncthreads();
     }
-    if (tid < f) dinv[tid] = 1.0 / A[(size_t)tid * ld + tid];
-    __syncthreads();
-    // ---- L^-1 column by column (forward substitution); CW_LPR lanes share a column
-    for (int ps = 0; ps < passes && ps < 2; ++ps) {
-        const int j = ps * CW_ROWS + rg;
-        const bool live = j < f;
-        double* zrow = A + (size_t)(live ? j : 0) * ld;  // z_i (i > j) lives at A[j][i]
-        const double zj = live ? dinv[j] : 0.0;
-        for (int i = 0; i < f; ++i) {  // uniform trip count: the shuffles below need the whole warp
-            double acc = 0.0;
-            if (live && i > j) {
-                const double* ai = A + (size_t)i * ld;
-                for (int k = j + 1 + q; k < i; k += CW_LPR) acc = fma(ai[k], zrow[k], acc);
-                if (q == 0) acc = fma(ai[j], zj, acc);
+    // ---- L^-1 column by column (forward substitution): z_j = 1/L_jj, z_i = -(sum_{j<=k<i} L_ik z_k) / L_ii
+    if (tid < f) {
+        const int j = tid;
+        double* zrow = A + (size_t)j * ld;   // z_i (i > j) lives at A[j][i]
+        const double zj = dinv[j];
+        for (int r = j + 1; r < f; ++r) {
+            const double* ar = A + (size_t)r * ld;
+            double a0 = ar[j] * zj, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = j + 1;
+            for (; k + 4 <= r; k += 4) {
+                a0 = fma(ar[k], zrow[k], a0);
+                a1 = fma(ar[k + 1], zrow[k + 1], a1);
+                a2 = fma(ar[k + 2], zrow[k + 2], a2);
+                a3 = fma(ar[k + 3], zrow[k + 3], a3);
             }
-            acc += shfl_xor_d(acc, 1);
-            acc += shfl_xor_d(acc, 2);
-            acc += shfl_xor_d(acc, 4);
-            if (live && i > j && q == 0) zrow[i] = -acc * dinv[i];
-            __syncwarp();
+            for (; k < r; ++k) a0 = fma(ar[k], zrow[k], a0);
+            zrow[r] = -((a0 + a1) + (a2 + a3)) * dinv[r];
         }
     }
     __syncthreads();
@@ -119,6 +107,7 @@ chol_whiten_kernel(const float* __restrict__ G, int f, int FP, double* __restric
         Mw[e] = w;
         Mu[e] = u;
     }
+    for (int e = tid; e < f * f; e += CW_THREADS) eye[e] = (e / f == e % f) ? 1.0f : 0.0f;  // the whitened G (ld = f)
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -224,13 +213,13 @@ size_t whiten_scratch_bytes(int f) {  // double f x (f|1) + f, used when the mat
     return align_up(((size_t)f * (f | 1) + f) * sizeof(double), 256);
 }
 
-int chol_whiten(const float* G, int f, int FP, void* scratch, float* Mw, float* Mu, int* flags, cudaStream_t st) {
+int chol_whiten(const float* G, int f, int FP, void* scratch, float* Mw, float* Mu, float* eye, int* flags, cudaStream_t st) {
     const size_t need = ((size_t)f * (f | 1) + f) * sizeof(double);
     const int use_smem = need <= 200 * 1024 ? 1 : 0;
     if (use_smem)
         WMF_CUDA(cudaFuncSetAttribute(chol_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     chol_whiten_kernel<<<1, CW_THREADS, use_smem ? need : 0, st>>>(G, f, FP, reinterpret_cast<double*>(scratch), use_smem,
-                                                                    Mw, Mu, flags);
+                                                                    Mw, Mu, eye, flags);
     WMF_LAUNCH_CHECK("chol_whiten_kernel");
     return WMF_OK;
 }
