@@ -47,6 +47,9 @@ extern "C" {
 
 const char* wmf_last_error(void);
 int wmf_version(void);
+/* Kernel launches this library has issued in this process so far (launch sites counted where they are
+ * issued; replays of a captured CUDA graph are not seen here: multiply the count of the capture). */
+long long wmf_launch_count(void);
 /* 0 if a usable sm_100 device is current, else WMF_ERR_NO_DEVICE. Fills sm_count if non-null. */
 int wmf_device_check(int* sm_count);
 
@@ -73,6 +76,15 @@ int64_t wmf_gram_blocks(int64_t n);
 int wmf_gram_partials(const float* Y, int64_t row0, int64_t nloc, int64_t n, int f, int64_t ldy, int ones_col0,
                       void* partials, size_t partials_bytes, void* stream);
 int wmf_gram_reduce(const void* partials, int64_t n, int f, float lambda, float* G, void* stream);
+
+/* Exchange step of a row-sharded half-step over peer memory (replaces an NCCL all-gather of the
+ * new factor shard and an all-reduce of Gram block partials). Copies `bytes` bytes at `src` (local memory) to byte
+ * offset dst_offset_bytes of each of `world` buffers whose PEER-MAPPED base addresses are in the device table
+ * peer_bases_dev[world] (symmetric allocations, e.g. torch.distributed._symmetric_memory buffer_ptrs); rank `self`
+ * (-1: none) is skipped because the source already lives in its copy. Stores go over NVLink as posted writes; the
+ * caller orders them before the readers with one cross-rank barrier per half-step. */
+int wmf_peer_broadcast(const void* src, size_t bytes, const void* const* peer_bases_dev, int world, int self,
+                       size_t dst_offset_bytes, void* stream);
 
 /* K2. One ALS half-step over `rows` CSR rows:            replaces the row loops at
  * wmf_model.py:220-239 (recompute_factors), :337-350 (recompute_factors_bias) and the Pool

@@ -21,6 +21,7 @@ _p, _i64, _i32, _f32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctype
 SIGNATURES = {
     "wmf_last_error": (ctypes.c_char_p, []),
     "wmf_version": (_i32, []),
+    "wmf_launch_count": (ctypes.c_longlong, []),
     "wmf_device_check": (_i32, [ctypes.POINTER(ctypes.c_int)]),
     "wmf_preprocess": (_i32, [_p, _i64, _i32, _f32, _f32, _p]),
     "wmf_gram_workspace_bytes": (_sz, [_i64, _i32]),
@@ -29,6 +30,7 @@ SIGNATURES = {
     "wmf_gram_blocks": (_i64, [_i64]),
     "wmf_gram_partials": (_i32, [_p, _i64, _i64, _i64, _i32, _i64, _i32, _p, _sz, _p]),
     "wmf_gram_reduce": (_i32, [_p, _i64, _i32, _f32, _p, _p]),
+    "wmf_peer_broadcast": (_i32, [_p, _sz, _p, _i32, _i32, _sz, _p]),
     "wmf_als_half_step_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "wmf_als_dual_max_entries": (_i32, []),
     "wmf_als_half_step_status": (_i32, [_p, _p, _p, _p]),

@@ -25,6 +25,10 @@ int check_cuda(cudaError_t e, const char* what) {
     return WMF_ERR_CUDA;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long& g_launches_ref() { return g_launches; }
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -56,7 +60,9 @@ extern "C" {
 
 const char* wmf_last_error(void) { return g_err; }
 
-int wmf_version(void) { return 100; }
+int wmf_version(void) { return 200; }
+
+long long wmf_launch_count(void) { return (long long)__atomic_load_n(&wmf::g_launches_ref(), __ATOMIC_RELAXED); }
 
 int wmf_device_check(int* sms) {
     int n = 0;

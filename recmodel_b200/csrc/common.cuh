@@ -10,6 +10,8 @@ namespace wmf {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int sm_count();
+void count_launch();   // process-wide count of kernel launches issued by this library (wmf_launch_count)
+unsigned long long& g_launches_ref();
 
 #define WMF_CUDA(call)                                        \
     do {                                                      \
@@ -19,6 +21,7 @@ int sm_count();
 
 #define WMF_LAUNCH_CHECK(name)                                \
     do {                                                      \
+        ::wmf::count_launch();                                \
         int _rc = ::wmf::check_cuda(cudaGetLastError(), name);\
         if (_rc) return _rc;                                  \
     } while (0)

@@ -144,43 +144,72 @@ __global__ void tc_prep_rows_kernel(HalfStepParams p, int4* __restrict__ tab, in
                                     int4* __restrict__ dtab, uint32_t* __restrict__ hdr_u, int64_t extra_slot0,
                                     int max_extra, int max_parts, int SPLIT_LEN, int primal_ok) {
     const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (s >= p.sched_len) return;
-    const int64_t row = p.row_order ? p.row_order[s] : s;
-    int4 e = make_int4(-1, 0, 0, 0), de = make_int4(-1, 0, 0, 0);
-    if (row >= 0) {
-        const int64_t lo = p.indptr[row], hi = p.indptr[row + 1];
-        int64_t n = hi - lo;
-        float m = 0.0f;
-        bool neg = false, zero = false;
-        // eight loads in flight per lane: the longest row of the matrix is this kernel's critical path
-        for (int64_t i0 = lo + lane; i0 < hi; i0 += 32 * 8) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ int64_t sh_lo[8], sh_hi[8];
+    __shared__ float sh_m[8][8];
+    __shared__ int sh_f[8][8];
+    const int64_t row = s < p.sched_len ? (p.row_order ? (int64_t)p.row_order[s] : s) : -1;
+    int64_t lo = 0, hi = 0;
+    if (row >= 0) { lo = p.indptr[row]; hi = p.indptr[row + 1]; }
+    // largest |weight| of the row, and whether a weight is negative (or NaN) / exactly zero. `stride` lanes walk the
+    // row with eight loads in flight each.
+    auto scan = [&](int64_t from, int64_t to, int first, int stride, float& m, int& flg) {
+        for (int64_t i0 = from + first; i0 < to; i0 += (int64_t)stride * 8) {
             float d[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int64_t i = i0 + 32 * u;
-                d[u] = i < hi ? __ldg(p.data + i) : 1.0f;
+                const int64_t i = i0 + (int64_t)stride * u;
+                d[u] = i < to ? __ldg(p.data + i) : 1.0f;
             }
             if (p.bias) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int64_t i = i0 + 32 * u;
-                    if (i < hi) d[u] = __fsub_rn(d[u], __ldg(p.Yraw + (int64_t)__ldg(p.indices + i) * p.ldraw));
+                    const int64_t i = i0 + (int64_t)stride * u;
+                    if (i < to) d[u] = __fsub_rn(d[u], __ldg(p.Yraw + (int64_t)__ldg(p.indices + i) * p.ldraw));
                 }
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                if (i0 + 32 * u < hi) {
-                    neg |= !(d[u] >= 0.0f);   // NaN weights go to the LU kernel too
-                    zero |= d[u] == 0.0f;
+                if (i0 + (int64_t)stride * u < to) {
+                    flg |= (!(d[u] >= 0.0f) ? 1 : 0) | (d[u] == 0.0f ? 2 : 0);   // NaN weights go to the LU kernel too
                     m = fmaxf(m, fabsf(d[u]));
                 }
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        neg = __any_sync(0xffffffffu, neg);
-        zero = __any_sync(0xffffffffu, zero);
+        for (int o = 16; o > 0; o >>= 1) {
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            flg |= __shfl_xor_sync(0xffffffffu, flg, o);
+        }
+    };
+    // Rows of up to COOP entries are scanned by their own warp; longer ones (they sit together at the head of a
+    // longest-first schedule) by the whole block, one after the other: the longest row of the matrix is this kernel's
+    // critical path (110 591 entries at ML-20M shape: 0.32 ms with one warp).
+    constexpr int COOP = 1024;
+    const bool big = hi - lo > COOP;
+    float m = 0.0f;
+    int flg = 0;
+    if (!big) scan(lo, hi, lane, 32, m, flg);
+    if (lane == 0) { sh_lo[w] = lo; sh_hi[w] = big ? hi : lo; }
+    __syncthreads();
+    for (int ww = 0; ww < 8; ++ww) {
+        const int64_t l = sh_lo[ww], h = sh_hi[ww];
+        if (h <= l) continue;  // uniform over the block
+        float m2 = 0.0f;
+        int f2 = 0;
+        scan(l, h, threadIdx.x, 256, m2, f2);
+        if (lane == 0) { sh_m[ww][w] = m2; sh_f[ww][w] = f2; }
+    }
+    __syncthreads();
+    if (big) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { m = fmaxf(m, sh_m[w][k]); flg |= sh_f[w][k]; }
+    }
+    if (s >= p.sched_len) return;
+    int4 e = make_int4(-1, 0, 0, 0), de = make_int4(-1, 0, 0, 0);
+    if (row >= 0) {
+        int64_t n = hi - lo;
+        const bool neg = (flg & 1) != 0, zero = (flg & 2) != 0;
         const bool g_bad = (hdr_u[1] & 8u) != 0;
         // the dual right-hand side (d+1)/sqrt(d) needs d > 0: a stored zero weight (it still adds y to the
         // right-hand side, wmf_model.py:239) keeps the row on the primal side

@@ -336,14 +336,20 @@ def gram_block_rows(n):
     return int(_lib.load().wmf_gram_block_rows(int(n)))
 
 
-def gram_partials(Y_local, row0, n_total, ones_col0=False):
+def gram_blocks(n):
+    """Number of Gram blocks of a matrix of n rows (a function of n alone)."""
+    return int(_lib.load().wmf_gram_blocks(int(n)))
+
+
+def gram_partials(Y_local, row0, n_total, ones_col0=False, out=None):
     """float64 [blocks, f, f] buffer holding the Gram partials of the blocks inside the local slice
-    (global rows [row0, row0 + len(Y_local))) and zeros elsewhere; see include/wmf_b200.h."""
+    (global rows [row0, row0 + len(Y_local))) and zeros elsewhere; see include/wmf_b200.h. ``out``: an existing
+    buffer of that shape (only the local blocks are written: the peer-memory exchange fills the others)."""
     lib = _lib.load()
     _f32(Y_local)
     nloc, f = Y_local.shape
     blocks = int(lib.wmf_gram_blocks(int(n_total)))
-    buf = torch.zeros((blocks, f, f), dtype=torch.float64, device=Y_local.device)
+    buf = out if out is not None else torch.zeros((blocks, f, f), dtype=torch.float64, device=Y_local.device)
     with _on(Y_local.device):
         _lib.check(lib.wmf_gram_partials(_ptr(Y_local), int(row0), nloc, int(n_total), f, Y_local.stride(0),
                                          int(bool(ones_col0)), _ptr(buf), buf.numel() * 8, _stream(Y_local.device)),
@@ -351,11 +357,21 @@ def gram_partials(Y_local, row0, n_total, ones_col0=False):
     return buf
 
 
-def gram_from_partials(partials, n_total, lam):
+def peer_broadcast(src, peer_table, world, self_rank, dst_offset_bytes):
+    """Write the contiguous tensor ``src`` to byte offset ``dst_offset_bytes`` of every peer's symmetric buffer
+    (``peer_table``: int64 device tensor of peer-mapped base addresses); include/wmf_b200.h: wmf_peer_broadcast."""
+    lib = _lib.load()
+    assert src.is_contiguous()
+    with _on(src.device):
+        _lib.check(lib.wmf_peer_broadcast(_ptr(src), src.numel() * src.element_size(), _ptr(peer_table), int(world),
+                                          int(self_rank), int(dst_offset_bytes), _stream(src.device)), "wmf_peer_broadcast")
+
+
+def gram_from_partials(partials, n_total, lam, out=None):
     """G from the (exchanged) block partials: blocks added in block order, rounded once, + lam I."""
     lib = _lib.load()
     f = partials.shape[1]
-    G = torch.empty((f, f), dtype=torch.float32, device=partials.device)
+    G = out if out is not None else torch.empty((f, f), dtype=torch.float32, device=partials.device)
     with _on(partials.device):
         _lib.check(lib.wmf_gram_reduce(_ptr(partials), int(n_total), f, float(lam), _ptr(G), _stream(partials.device)),
                    "wmf_gram_reduce")

@@ -1,15 +1,20 @@
 """One resident ALS epoch as four replayable CUDA graphs.
 
-An epoch is a fixed sequence of launches (Gram, schedule table, half-step kernel, conditional fix-up,
-and - row-sharded - the exchange of Gram blocks and factor shards). At ML-20M shape on 8 GPUs a half-step
-kernel runs for ~1 ms, so ~50 launches and collectives per epoch issued from Python leave the GPU waiting
-for the host; captured once, the same sequence replays with four graph launches per epoch.
+An epoch is a fixed sequence of launches (Cholesky of the Gram, whitening, schedule tables, the dual and primal
+tensor-core kernels, unwhitening, conditional fix-up, Gram of the new factors and - row-sharded - the exchange of
+factor rows and Gram blocks). At ML-20M shape on 8 GPUs a half-step runs for well under a millisecond, so the ~25
+launches per epoch issued from Python would leave the GPU waiting for the host; captured once, the same sequence
+replays with four graph launches per epoch.
 
-    user half-step | exchange (Gram of the new user shard, all-gather) | item half-step | exchange
+    user half-step | exchange (rows + Gram blocks of the new user shard) | item half-step | exchange
+
+Row-sharded, the exchange is the library's own kernel writing into every peer's symmetric copy of the factor and
+Gram-partial buffers over NVLink (``sharding.PeerBuffers``) followed by one barrier; where symmetric memory is not
+available it falls back to NCCL (all-gather of the rows, all-reduce of zero-padded Gram blocks).
 
 The graphs read and write fixed buffers (``items``, ``users``, ``G_items``, ``G_users``), so epoch k+1's first
-graph consumes what epoch k's last graph produced. Events can be recorded between the replays (the
-bench times the two half-step kernels that way). wmf_model.py:140-156 is the loop this replaces.
+graph consumes what epoch k's last graph produced. Events can be recorded between the replays (the bench times the
+two half-step stages that way). wmf_model.py:140-156 is the loop this replaces.
 """
 import torch
 
@@ -17,22 +22,35 @@ from . import _lib, engine, sharding
 
 
 class ResidentEpoch:
-    def __init__(self, C, CT, items0, gamma, bias=False, algo=_lib.ALGO_AUTO, ub=None, ib=None, graphs=True):
+    def __init__(self, C, CT, items0, gamma, bias=False, algo=_lib.ALGO_AUTO, ub=None, ib=None, graphs=True, peer=True):
         """C / CT: this rank's row slices (DeviceCSR) of the count matrix and of its transpose; ub / ib: shard
-        boundaries (None on one GPU); items0: full initial item factors on the device."""
+        boundaries (None on one GPU); items0: full initial item factors on the device; peer: exchange over peer
+        memory when it is available (else NCCL)."""
         self.C, self.CT, self.gamma, self.bias, self.algo = C, CT, float(gamma), bool(bias), algo
         self.ub, self.ib = ub, ib
         self.world = 1 if ub is None else len(ub) - 1
+        self.rank = sharding.dist_info()[0] if self.world > 1 else 0
         dev, f = items0.device, items0.shape[1]
         n_users = C.shape[0] if ub is None else int(ub[-1])
         n_items = CT.shape[0] if ib is None else int(ib[-1])
-        self.items = items0.clone()
-        self.users = torch.zeros((n_users, f), dtype=torch.float32, device=dev)
+        self.n_users, self.n_items = n_users, n_items
+        self.px = sharding.PeerBuffers.create(n_users, n_items, f, dev) if (self.world > 1 and peer) else None
+        if self.px is not None:
+            self.items, self.users = self.px.views["items"], self.px.views["users"]
+            self.items.copy_(items0)
+            self.users.zero_()
+            self.exchange_mode = "peer-memory stores (wmf_peer_broadcast) + 1 barrier per half-step"
+        else:
+            self.items = items0.clone()
+            self.users = torch.zeros((n_users, f), dtype=torch.float32, device=dev)
+            self.exchange_mode = "none (single GPU)" if self.world == 1 else "nccl all-gather + all-reduce"
         self.G_items = engine.gram(self.items, self.gamma, ones_col0=self.bias)
         self.G_users = torch.zeros_like(self.G_items)
-        self.ws = None
         if self.world == 1:   # the new factors ARE the full matrices: the half-steps write them in place
             self.X_users, self.X_items = self.users, self.items
+        elif self.px is not None:   # this rank's rows of the symmetric full matrices
+            self.X_users = self.users[int(ub[self.rank]):int(ub[self.rank + 1])]
+            self.X_items = self.items[int(ib[self.rank]):int(ib[self.rank + 1])]
         else:                 # this rank's new shards
             self.X_users = torch.empty((C.shape[0], f), dtype=torch.float32, device=dev)
             self.X_items = torch.empty((CT.shape[0], f), dtype=torch.float32, device=dev)
@@ -45,37 +63,58 @@ class ResidentEpoch:
         self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
         self.stages = [self._user_half_step, self._user_exchange, self._item_half_step, self._item_exchange]
         self.graphs = None
+        self.launches_per_epoch = 0
+        if self.px is not None:
+            torch.cuda.synchronize(dev)
+            self.px.barrier()     # every rank's initial items / zeroed users are in place before anyone pushes
         if graphs:
             self._capture()
+        else:
+            self._count_launches()
 
     # ---- the four stages (eager form; captured verbatim)
     def _user_half_step(self):
         engine.half_step(self.C, self.items, self.G_items, bias=self.bias, algo=self.algo, out=self.X_users, ws=self.ws)
 
-    def _user_exchange(self):
-        if self.world > 1:
-            self.G_users.copy_(sharding.sharded_gram(self.X_users, self.ub, self.gamma, ones_col0=self.bias))
-            sharding.all_gather_rows(self.X_users, self.ub, out=self.users)
+    def _exchange(self, X, bounds, n_total, name, G_out, full):
+        if self.px is not None:
+            lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
+            B = engine.gram_block_rows(n_total)
+            gp = self.px.views["gp_" + name]
+            self.px.push(name, lo, hi)                                        # new factor rows -> every peer
+            engine.gram_partials(X, lo, n_total, ones_col0=self.bias, out=gp)  # Gram blocks of the shard
+            self.px.push("gp_" + name, lo // B, -(-hi // B))                   # ... -> every peer
+            self.px.barrier()
+            engine.gram_from_partials(gp, n_total, self.gamma, out=G_out)      # all blocks in block order
+        elif self.world > 1:
+            G_out.copy_(sharding.sharded_gram(X, bounds, self.gamma, ones_col0=self.bias))
+            sharding.all_gather_rows(X, bounds, out=full)
         else:
-            engine.gram(self.users, self.gamma, ones_col0=self.bias, ws=self.ws, out=self.G_users)
+            engine.gram(full, self.gamma, ones_col0=self.bias, ws=self.ws, out=G_out)
+
+    def _user_exchange(self):
+        self._exchange(self.X_users, self.ub, self.n_users, "users", self.G_users, self.users)
 
     def _item_half_step(self):
         engine.half_step(self.CT, self.users, self.G_users, bias=self.bias, algo=self.algo, out=self.X_items, ws=self.ws)
 
     def _item_exchange(self):
-        if self.world > 1:
-            self.G_items.copy_(sharding.sharded_gram(self.X_items, self.ib, self.gamma, ones_col0=self.bias))
-            sharding.all_gather_rows(self.X_items, self.ib, out=self.items)
-        else:
-            engine.gram(self.items, self.gamma, ones_col0=self.bias, ws=self.ws, out=self.G_items)
+        self._exchange(self.X_items, self.ib, self.n_items, "items", self.G_items, self.items)
+
+    def _count_launches(self):
+        lib = _lib.load()
+        n0 = int(lib.wmf_launch_count())
+        for st in self.stages:
+            st()
+        self.launches_per_epoch = int(lib.wmf_launch_count()) - n0
 
     def _capture(self):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # warm-up on the capture stream: workspaces, attributes, NCCL channels
-            for _ in range(2):
-                for st in self.stages:
-                    st()
+            self._count_launches()
+            for st in self.stages:
+                st()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graphs = []
@@ -107,7 +146,3 @@ class ResidentEpoch:
         if events is not None:
             events[3].record()
         self.run_stage(3)
-
-    # launches of this repo's kernels per epoch (bench.py's gpu_launches): 2 x (tc_maxima, tc_prep_rows,
-    # tc_finish_prep, als_half_step_tc, conditional fix-up) + 2 x (gram_partial, gram_reduce)
-    KERNELS_PER_EPOCH = 14

@@ -88,3 +88,68 @@ def all_reduce_sum_(t, group=None):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+class PeerBuffers:
+    """Symmetric (peer-mapped) copies of everything a row-sharded epoch exchanges: the full user and item factor
+    matrices and the Gram block partials of both sides. Rank g writes the rows / blocks it owns into every peer's
+    copy with the library's own kernel (``engine.peer_broadcast`` -> wmf_peer_broadcast: posted stores over
+    NVLink / NVSwitch); one barrier per half-step orders the stores before the readers. No NCCL all-gather, no
+    all-reduce, and every rank adds ALL Gram blocks in block order: the bits of the single-GPU Gram.
+    ``create`` returns None where symmetric memory is unavailable (CPU / gloo tests): callers fall back to
+    ``all_gather_rows`` / ``sharded_gram``."""
+
+    def __init__(self, handle, flat, views, table, rank, world):
+        self.handle, self.flat, self.views, self.table, self.rank, self.world = handle, flat, views, table, rank, world
+
+    @classmethod
+    def create(cls, n_users, n_items, f, device, group=None):
+        from . import engine
+        rank, world = dist_info(group)
+        if world == 1 or device.type != "cuda":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+        except Exception:
+            return None
+        bu, bi = engine.gram_blocks(n_users), engine.gram_blocks(n_items)
+        sizes = {"users": n_users * f * 4, "items": n_items * f * 4, "gp_users": bu * f * f * 8, "gp_items": bi * f * f * 8}
+        offs, total = {}, 0
+        for k, nb in sizes.items():
+            offs[k] = total
+            total += (nb + 255) // 256 * 256
+        try:
+            flat = symm.empty(total, dtype=torch.uint8, device=device)
+            grp = group if group is not None else dist.group.WORLD
+            try:
+                handle = symm.rendezvous(flat, group=grp)
+            except TypeError:
+                handle = symm.rendezvous(flat, grp.group_name)
+            ptrs = [int(x) for x in handle.buffer_ptrs]
+        except Exception as exc:  # no peer access / unsupported allocator: NCCL path
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({type(exc).__name__}: {exc}); exchanging factor shards with NCCL")
+            return None
+        views = {
+            "users": flat[offs["users"]:offs["users"] + sizes["users"]].view(torch.float32).view(n_users, f),
+            "items": flat[offs["items"]:offs["items"] + sizes["items"]].view(torch.float32).view(n_items, f),
+            "gp_users": flat[offs["gp_users"]:offs["gp_users"] + sizes["gp_users"]].view(torch.float64).view(bu, f, f),
+            "gp_items": flat[offs["gp_items"]:offs["gp_items"] + sizes["gp_items"]].view(torch.float64).view(bi, f, f),
+        }
+        table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        out = cls(handle, flat, views, table, rank, world)
+        out.offs = offs
+        return out
+
+    def push(self, name, lo, hi):
+        """Rows (factors) or blocks (Gram partials) [lo, hi) of this rank's copy of ``name`` -> every peer's copy."""
+        from . import engine
+        v = self.views[name]
+        if hi <= lo:
+            return
+        part = v[lo:hi]
+        row_bytes = part[0].numel() * part.element_size()
+        engine.peer_broadcast(part, self.table, self.world, self.rank, self.offs[name] + lo * row_bytes)
+
+    def barrier(self):
+        self.handle.barrier(channel=0)

@@ -19,6 +19,7 @@ SHAPES = {
     "cfg2": (138_493, 26_744, 20_000_000, 128, False),  # ML-20M shape, 1 B200
     "cfg3": (480_189, 17_770, 100_000_000, 128, False),  # Netflix shape
     "cfg4": (10_000_000, 1_000_000, 1_000_000_000, 256, False),
+    "cfg4_scaled": (1_000_000, 100_000, 100_000_000, 256, False),   # config 4 at 1/10 of every dimension (one GPU)
 }
 
 
@@ -102,6 +103,39 @@ def make_counts(n_users, n_items, nnz, seed=DEFAULT_SEED, planted_rank=0, expone
     mat = scipy.sparse.csr_matrix((vals, cols, indptr.astype(idx_dtype)), shape=(n_users, n_items))
     mat.has_sorted_indices = True  # keys are sorted, so columns ascend inside each row
     return mat
+
+
+def make_counts_device(n_users, n_items, nnz, device, seed=DEFAULT_SEED, exponent=0.8, sigma=1.0):
+    """``make_counts`` with the same recipe generated ON THE DEVICE (log-normal user activity, item popularity
+    ~ rank^-exponent, distinct pairs, counts 1..5), for the shapes whose host generation takes minutes (Netflix
+    shape, the 1 B-entry power-law config and its scaled version). Returns (indptr int64, indices int32, data
+    float32) CUDA tensors of a CSR matrix with sorted indices; deterministic in ``seed`` on a given GPU model.
+    torch is used for data generation only (not a product path)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    act = torch.exp(sigma * torch.randn(n_users, device=device, generator=g, dtype=torch.float64))
+    cum_u = torch.cumsum(act / act.sum(), 0)
+    pop = torch.arange(1, n_items + 1, device=device, dtype=torch.float64) ** -exponent
+    pop = pop[torch.randperm(n_items, device=device, generator=g)]
+    cum_i = torch.cumsum(pop / pop.sum(), 0)
+    keys = torch.empty(0, dtype=torch.int64, device=device)
+    rounds = 0
+    while keys.numel() < nnz and rounds < 40:
+        m = int((nnz - keys.numel()) * 1.3) + 1024
+        u = torch.searchsorted(cum_u, torch.rand(m, device=device, generator=g, dtype=torch.float64)).clamp_(max=n_users - 1)
+        i = torch.searchsorted(cum_i, torch.rand(m, device=device, generator=g, dtype=torch.float64)).clamp_(max=n_items - 1)
+        keys = torch.unique(torch.cat([keys, u * n_items + i]))
+        del u, i
+        rounds += 1
+    if keys.numel() > nnz:
+        keys = keys[torch.randperm(keys.numel(), device=device, generator=g)[:nnz]].sort().values
+    rows = keys // n_items
+    cols = (keys % n_items).to(torch.int32)
+    indptr = torch.zeros(n_users + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n_users), 0)
+    data = torch.randint(1, 6, (keys.numel(),), device=device, generator=g).to(torch.float32)
+    return indptr, cols, data
 
 
 def split_train_test(matrix, train=0.8, seed=1993):
