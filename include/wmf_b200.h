@@ -56,6 +56,15 @@ int wmf_device_check(int* sm_count);
 /* K6. In-place count preprocessing.                      replaces wmf_model.py:66-70,119-123 */
 int wmf_preprocess(float* data, int64_t nnz, int mode, float alpha, float beta, void* stream);
 
+/* N1. CSR of the transpose, on the device:             replaces count_mat.T.tocsr() (wmf_model.py:128).
+ * A stable radix sort of the entries by column: every output row holds ascending original row ids (SciPy's
+ * order), whatever the column order inside the input rows; duplicate entries are kept. Transposing twice
+ * canonicalises a matrix (sorted indices). out_indptr int64[cols+1], out_indices int32[nnz], out_data float[nnz]. */
+size_t wmf_csr_transpose_workspace_bytes(int64_t rows, int64_t cols, int64_t nnz);
+int wmf_csr_transpose(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows, int64_t cols,
+                      int64_t nnz, int64_t* out_indptr, int32_t* out_indices, float* out_data, void* ws,
+                      size_t ws_bytes, void* stream);
+
 /* K1. G = Y^T Y + lambda*I  (f x f, row-major, ld = f).  replaces np.dot(Y.T,Y)+lambda*eye at
  * wmf_model.py:215,244,258,332 (and the Gram inside :85,:88). ones_col0 != 0 computes with
  * column 0 of Y replaced by 1 (the bias path's Y[:,0] = 1, :331) without touching Y.

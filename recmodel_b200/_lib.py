@@ -24,6 +24,8 @@ SIGNATURES = {
     "wmf_launch_count": (ctypes.c_longlong, []),
     "wmf_device_check": (_i32, [ctypes.POINTER(ctypes.c_int)]),
     "wmf_preprocess": (_i32, [_p, _i64, _i32, _f32, _f32, _p]),
+    "wmf_csr_transpose_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "wmf_csr_transpose": (_i32, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "wmf_gram_workspace_bytes": (_sz, [_i64, _i32]),
     "wmf_gram": (_i32, [_p, _i64, _i32, _i64, _f32, _i32, _p, _p, _sz, _p]),
     "wmf_gram_block_rows": (_i64, [_i64]),

@@ -45,5 +45,9 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
 // dual (n x n) kernel for the rows of the dual table (half_step_dual.cu)
 int tc_dual_launch(const HalfStepParams& p, const int4* dtab, const uint32_t* hdr_u, int grid, cudaStream_t st);
 int tc_dual_max_entries();
+// primal kernel for 128 < f <= 256 (half_step_tc256.cu); same tables and scratch conventions as the 128-wide one
+size_t tc256_part_floats();
+int tc256_launch(const HalfStepParams& p, const int4* tab, const int4* segtab, float* parts, int* counters,
+                 const uint32_t* hdr_u, int64_t extra_slot0, int* flags, int grid, cudaStream_t st);
 
 }  // namespace wmf

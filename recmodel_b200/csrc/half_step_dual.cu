@@ -61,10 +61,6 @@ constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(ND_MAX % 16 == 0 && ND_MAX <= 128, "dual rows must fit the TMEM lanes");  // the kernel itself takes any n <= 128
 
-__device__ __forceinline__ void sts2u(uint32_t a, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
-}
-
 __global__ void __launch_bounds__(THREADS, 1)
 als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const uint32_t* __restrict__ hdr_u,
                           int* __restrict__ flags) {

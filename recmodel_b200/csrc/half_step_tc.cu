@@ -135,8 +135,7 @@ constexpr size_t PART_FLOATS = (size_t)F * F + F;  // a segment's S^2 W (chunk-m
 //   a negative weight (bias formula, d~ = d - beta, wmf_model.py:343), or G itself not positive definite
 //                                  -> fix-up list: the CUDA-core LU kernel solves it after the tensor-core kernels
 //   at most nd_max entries         -> dual table (half_step_dual.cu: n x n system)
-//   otherwise                      -> primal table (this file: f x f system); wider than 128 features there is no
-//                                     primal tensor-core kernel yet and the row joins the fix-up list
+//   otherwise                      -> primal table (f x f system: this file for f <= 128, half_step_tc256.cu above)
 // Rows longer than SPLIT_LEN are cut into equal segments (a function of the row length only, so a row's
 // arithmetic never depends on the launch it is in): segment 0 stays in the row's slot, the others go to
 // extra slots behind the schedule, which the persistent CTAs reach round-robin like every other slot.
@@ -865,7 +864,8 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
 
 // f <= 256: every width goes through the whitened pipeline (factors padded to 128 or 256 columns). Rows with at
 // most tc_dual_max_entries() stored entries take the dual kernel at any width; longer rows take the primal kernel
-// of this file when f <= 128 and the CUDA-core kernel above that. Biases are a shifted weight (wmf_model.py:343).
+// of this file when f <= 128 and the 256-wide one (half_step_tc256.cu) above that. Biases are a shifted weight
+// (wmf_model.py:343); only rows with a negative weight go to the CUDA-core LU kernel.
 bool tc_half_step_supported(int f, int bias) { return f >= 1 && f <= 256 && (!bias || f >= 2); }
 
 // Workspace (bytes from a 256-aligned base):
@@ -883,6 +883,7 @@ struct TcLayout {
         off_simt, off_parts, total;
 };
 static int tc_fp(int f) { return f <= 128 ? 128 : 256; }
+static size_t part_floats(int f) { return f <= F ? PART_FLOATS : tc256_part_floats(); }  // a parked segment: matrix + rhs
 static TcLayout tc_layout(int64_t sched_slots, int64_t rows, int64_t cols, int f, int64_t parts) {
     TcLayout L;
     const size_t FP = (size_t)tc_fp(f);
@@ -902,12 +903,11 @@ static TcLayout tc_layout(int64_t sched_slots, int64_t rows, int64_t cols, int f
     L.off_xp = align_up(L.off_yt + (size_t)cols * FP * sizeof(float), 256);
     L.off_simt = align_up(L.off_xp + (size_t)rows * FP * sizeof(float), 256);
     L.off_parts = align_up(L.off_simt + simt_half_step_workspace_bytes(f), 256);
-    L.total = L.off_parts + (size_t)L.max_parts * PART_FLOATS * sizeof(float);
+    L.total = L.off_parts + (size_t)L.max_parts * part_floats(f) * sizeof(float);
     return L;
 }
 size_t tc_half_step_workspace_bytes(int64_t rows, int64_t cols, int f, int, int64_t segments) {
     if (segments < 0) segments = rows >= 1024 ? DEFAULT_PARTS : 128;
-    if (f > F) segments = 0;  // only the 128-wide primal kernel splits rows
     return tc_layout(2 * rows + 4096 + 1024, rows, cols, f, segments + 2).total;
 }
 
@@ -926,7 +926,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
         return WMF_ERR_WORKSPACE;
     }
     // whatever is left after the fixed regions is scratch for the segments of split rows (each needs 34 bytes of tables too)
-    int64_t max_parts = in.f <= F ? (int64_t)((ws_bytes - need) / (PART_FLOATS * sizeof(float) + 34 + 8)) - 4 : 0;
+    int64_t max_parts = (int64_t)((ws_bytes - need) / (part_floats(in.f) * sizeof(float) + 34 + 8)) - 4;
     if (max_parts < 2) max_parts = 0;
     if (max_parts > (1ll << 24)) max_parts = 1ll << 24;
     const TcLayout L = tc_layout(extra_slot0, in.rows, in.cols, in.f, max_parts);
@@ -962,7 +962,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     p.fix_count = reinterpret_cast<int*>(hdr_u + 8);
     p.nd_max = dual_enabled() ? tc_dual_max_entries() : 0;
     p.prof = profile_enabled() ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
-    const int primal_ok = in.f <= F ? 1 : 0;
+    const int primal_ok = 1;   // 128-wide kernel of this file, or the 256-wide one (half_step_tc256.cu)
     tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, segtab, dtab, hdr_u, extra_slot0,
                                                                             (int)max_parts, (int)max_parts, split_len(),
                                                                             primal_ok);
@@ -973,7 +973,10 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
         rc = tc_dual_launch(p, dtab, hdr_u, grid, st);
         if (rc) return rc;
     }
-    if (primal_ok) {
+    if (in.f > F) {
+        rc = tc256_launch(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags, grid, st);
+        if (rc) return rc;
+    } else {
         // the attribute is per device: set it on every call (a process may drive several GPUs)
         if (p.prof) {
 #ifdef WMF_TC_PROFILE_BUILD

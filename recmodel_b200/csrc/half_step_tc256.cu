@@ -1,0 +1,513 @@
+// K2 (tcgen05, primal form, 128 < f <= 256): ALS rows with more stored entries than the dual kernel takes.
+// Replaces the per-row loop of recompute_factors / recompute_factors_bias (wmf_model.py:220-239, :337-350) for
+// BASELINE.json's config 4 (dim 256) and for dim 128 with biases (f = 129).
+//
+// Same arithmetic as half_step_tc.cu on the whitened factors: (I + sum_j d_j y~_j y~_j^T) x' = sum_j (d_j+1) y~_j,
+// FP16 hi/lo split Gram on the tensor cores, block Gauss-Jordan in TMEM. A 256 x 256 fp32 matrix IS the tensor
+// memory of an SM (128 lanes x 512 columns): matrix rows 0-127 live in columns [0, 256), rows 128-255 in columns
+// [256, 512), so one row of the count matrix is in flight per SM and the roles are
+//   warps 0-7   solve    thread t owns matrix row t (TMEM lane t % 128, column base 256 * (t / 128))
+//   warps 8-11  gather   warp w stages the full 1 KB factor rows of entries 8w .. 8w+7 of each 32-entry sub-chunk
+//               (cp.async), every lane then converts its 2 x 4 features of each row and stores 8-byte pieces of the
+//               ENTRY-major operand tile (tcgen05 "MN-major": an entry's features are contiguous, 64 per 128-byte
+//               swizzle row; scripts/probe/mma_mn_major_probe.cu): no transposition through shared memory
+//   warp 12     MMA      per 16 entries 3 products x 2 matrix halves: M = 128, N = f rounded to 16, K = 16
+// Long rows are cut into segments that different CTAs accumulate (partials parked in L2/HBM, summed in segment
+// order with round-to-nearest adds by the group that parks the last one): the tensor core truncates its fp32
+// accumulation, and a power-law head row (600 k entries at the scaled config-4 shape) is a whole SM's share of the
+// half-step. The schedule tables, segment tables and the fix-up list are the ones tc_prep_rows_kernel writes.
+#include "tc_common.cuh"
+#include "half_step.cuh"
+#include "factor8.cuh"
+
+namespace wmf {
+
+namespace p256 {
+
+using namespace tc;
+
+constexpr int F = 256;
+constexpr int SUB = 32;
+constexpr int NSTAGE = 3;
+constexpr int NSTG = 2;                       // raw buffers per gather warp (cp.async depth)
+constexpr int NGW = 4;                        // gather warps
+constexpr int TILE_SBO = 1024;                // next 8 entries (K)
+constexpr int TILE_LBO = (SUB / 8) * TILE_SBO;    // next 64 features: 4 KB
+constexpr int TILE_BYTES = (F / 64) * TILE_LBO;   // 32 entries x 256 fp16 features = 16 KB
+constexpr int PAIR_BYTES = 2 * TILE_BYTES;    // [zh ; zl]
+constexpr int WSTG_BYTES = 8 * F * 4;         // a gather warp's raw buffer: its 8 entries x 256 fp32 features, 8 KB
+constexpr int NB = 8;
+constexpr int SOLVERS = 256;
+constexpr int GATHER_WARP0 = SOLVERS / 32, MMA_WARP = GATHER_WARP0 + NGW;
+constexpr int THREADS = (MMA_WARP + 1) * 32;  // 416
+constexpr uint32_t TMEM_COLS = 512;
+
+constexpr int PANEL_TILE_BYTES = F * NB * 4;  // 8 KB: 256 rows x 8 fp32, K-major, no swizzle
+constexpr int OFF_STAGES = 0;
+constexpr int OFF_STG = OFF_STAGES + NSTAGE * PAIR_BYTES;
+constexpr int OFF_TILEH = OFF_STG + NGW * NSTG * WSTG_BYTES;
+constexpr int OFF_TILEL = OFF_TILEH + PANEL_TILE_BYTES;
+constexpr int OFF_NINV = OFF_TILEL + PANEL_TILE_BYTES;              // 32 blocks x (8 x 8) floats
+constexpr int OFF_ZB = OFF_NINV + (F / NB) * NB * NB * 4;
+constexpr int OFF_DBLK = OFF_ZB + (F / NB) * NB * 4;
+constexpr int OFF_BFIN = OFF_DBLK + (NB * NB + 2 * NB) * 4;
+constexpr int OFF_BVEC = ((OFF_BFIN + F * 4 + 127) / 128) * 128;    // NGW x F floats (rhs partials)
+constexpr int OFF_BARS = OFF_BVEC + NGW * F * 4;
+constexpr int NBARS = 2 * NSTAGE + 5;
+constexpr int OFF_TMEM_PTR = OFF_BARS + NBARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(OFF_STG % 1024 == 0 && OFF_TILEH % 128 == 0 && OFF_BARS % 8 == 0, "alignment");
+constexpr size_t PART_FLOATS = (size_t)F * F + F;   // a segment's S^2 W (chunk-major) and its rhs partial
+
+__global__ void __launch_bounds__(THREADS, 1)
+als_half_step_tc256_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const int4* __restrict__ segtab,
+                           float* __restrict__ parts, int* __restrict__ counters, const uint32_t* __restrict__ hdr_u,
+                           int64_t extra_slot0, int* __restrict__ flags) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + OFF_BARS;
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+    const uint32_t bar_acc_full = bars + 8u * (2 * NSTAGE), bar_acc_empty = bar_acc_full + 8u, bar_b_empty = bar_acc_full + 16u,
+                   bar_panel = bar_acc_full + 24u, bar_b_full = bar_acc_full + 32u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), NGW); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_acc_full, 1);
+        mbar_init(bar_acc_empty, SOLVERS);
+        mbar_init(bar_b_empty, SOLVERS);
+        mbar_init(bar_panel, 1);
+        mbar_init(bar_b_full, NGW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t tmem_ptr_addr = smem_base + OFF_TMEM_PTR;
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    // slots: first the extra slots (segments of split rows, behind the schedule in the table), then the schedule
+    const int ts = (int)gridDim.x;
+    const int total_slots = (int)hdr_u[4];
+    const int nextra = (total_slots - (int)extra_slot0 - (int)blockIdx.x + ts - 1) / ts;
+    const int sched_end = min((int)extra_slot0, ((int)hdr_u[9] + ts - 1) / ts * ts);
+    const int nslots = nextra + (sched_end - (int)blockIdx.x + ts - 1) / ts;
+    const int base_x = (int)extra_slot0 + (int)blockIdx.x, base_s = (int)blockIdx.x - nextra * ts;
+    auto ent_at = [&](int k) -> RowEnt {
+        RowEnt e{-1, 0, 0, 0, -1};
+        if (k < nslots) {
+            const int slot = k * ts + (k < nextra ? base_x : base_s);
+            e = unpack_ent(__ldg(rowtab + slot), slot);
+        }
+        return e;
+    };
+    const int f8 = p.f8, f16 = p.f16;
+
+    if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
+        // =============================== GATHER ===============================
+        const int gw = warp - GATHER_WARP0;
+        struct Raw { int idx; float sq; float dp1; };
+        // cursor over (row, sub-chunk)
+        int cu_k = -1, cu_c = 0, cu_nsub = 0, cu_n = 0, cu_gi = -1;
+        int64_t cu_lo = 0;
+        float cu_S = 1.0f;
+        RowEnt w0 = ent_at(0);
+        auto advance = [&]() {   // to the next sub-chunk; cu_k >= nslots: none left
+            ++cu_c;
+            ++cu_gi;
+            while (cu_k < nslots && cu_c >= cu_nsub) {
+                ++cu_k;
+                if (cu_k >= nslots) break;
+                const RowEnt e = w0;
+                w0 = ent_at(cu_k + 1);
+                cu_c = 0;
+                cu_nsub = 0;
+                if (e.n > 0) { cu_n = e.n; cu_lo = e.lo; cu_nsub = (e.n + SUB - 1) / SUB; cu_S = exp2f((float)e.sexp); }
+            }
+        };
+        auto load_raw = [&]() {
+            Raw rw{-1, 0.f, 0.f};
+            if (cu_k < nslots) {
+                const int off = cu_c * SUB + lane;
+                if (off < cu_n) {
+                    float d = __ldg(p.data + cu_lo + off);
+                    rw.idx = __ldg(p.indices + cu_lo + off);
+                    if (p.bias) d = __fsub_rn(d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
+                    rw.sq = cu_S * sqrtf(d);
+                    rw.dp1 = __fadd_rn(d, 1.0f);
+                }
+            }
+            return rw;
+        };
+        auto issue = [&](const Raw& rw, int buf) {  // this warp's 8 rows of the sub-chunk -> raw buffer
+            __syncwarp();
+            const uint32_t dst0 = smem_base + OFF_STG + (gw * NSTG + buf) * WSTG_BYTES + lane * 16;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int idx = __shfl_sync(0xffffffffu, rw.idx, 8 * gw + e);
+                const float* src = p.Y + (int64_t)(idx >= 0 ? idx : 0) * F + lane * 4;
+                cp_async16(dst0 + e * 1024, src, idx >= 0 ? 16u : 0u);            // features 4 lane .. 4 lane + 3
+                cp_async16(dst0 + e * 1024 + 512, src + 128, idx >= 0 ? 16u : 0u);  // features 128 + 4 lane ..
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // state of a sub-chunk that the later pipeline steps need: global index, row end marker
+        struct Desc { int gi; int last; };
+        auto describe = [&]() -> Desc { return cu_k >= nslots ? Desc{-1, 0} : Desc{cu_gi, cu_c + 1 >= cu_nsub ? 1 : 0}; };
+        const uint32_t chunk = ((uint32_t)lane & 15u) >> 1, half8 = ((uint32_t)lane & 1u) * 8u, fb0 = (uint32_t)lane >> 4;
+        cu_c = -1;
+        advance();
+        Desc d0 = describe();
+        Raw r0 = load_raw();
+        issue(r0, 0);
+        advance();
+        Desc d1 = describe();
+        Raw r1 = load_raw();
+        advance();
+        uint32_t j = 0, row_n = 0;
+        float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        while (d0.gi >= 0) {
+            const Desc d2 = describe();
+            issue(r1, (j + 1) & 1);
+            const Raw r2 = load_raw();
+            advance();
+            const int s = d0.gi % NSTAGE, sb = j & 1;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            mbar_wait(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
+            const uint32_t stg = smem_base + OFF_STG + (gw * NSTG + sb) * WSTG_BYTES + lane * 16;
+            // entry e of this warp is entry 8 gw + e of the sub-chunk: K group gw, row e of the swizzle atom
+            const uint32_t tile = smem_base + OFF_STAGES + s * PAIR_BYTES + gw * TILE_SBO + half8;
+            float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float sq = __shfl_sync(0xffffffffu, r0.sq, 8 * gw + e);
+                const float dp = __shfl_sync(0xffffffffu, r0.dp1, 8 * gw + e);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // features 128 h + 4 lane ..: feature block 2 h + lane / 16
+                    const float4 v = lds4(stg + e * 1024 + h * 512);
+                    const float z0 = sq * v.x, z1 = sq * v.y, z2 = sq * v.z, z3 = sq * v.w;
+                    part[4 * h + 0] = fmaf(dp, v.x, part[4 * h + 0]); part[4 * h + 1] = fmaf(dp, v.y, part[4 * h + 1]);
+                    part[4 * h + 2] = fmaf(dp, v.z, part[4 * h + 2]); part[4 * h + 3] = fmaf(dp, v.w, part[4 * h + 3]);
+                    const __half2 h01 = __floats2half2_rn(z0, z1), h23 = __floats2half2_rn(z2, z3);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(z0 - f01.x, z1 - f01.y), l23 = __floats2half2_rn(z2 - f23.x, z3 - f23.y);
+                    const uint32_t a = tile + (2u * h + fb0) * TILE_LBO + e * 128 + ((chunk ^ (uint32_t)e) << 4);
+                    sts2u(a, h2_bits(h01), h2_bits(h23));
+                    sts2u(a + TILE_BYTES, h2_bits(l01), h2_bits(l23));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bacc[i] += part[i];
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full(s));
+            if (d0.last) {  // hand this warp's rhs partial to the solvers
+                mbar_wait(bar_b_empty, (row_n & 1u) ^ 1u);
+                const uint32_t bv = smem_base + OFF_BVEC + (gw * F + lane * 4) * 4;
+                sts4(bv, bacc[0], bacc[1], bacc[2], bacc[3]);
+                sts4(bv + 128 * 4, bacc[4], bacc[5], bacc[6], bacc[7]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_b_full);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bacc[i] = 0.f;
+                ++row_n;
+            }
+            ++j;
+            d0 = d1; d1 = d2;
+            r0 = r1; r1 = r2;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp == MMA_WARP) {
+        // =============================== GRAM MMA ISSUE ===============================
+        if (lane == 0) {
+            uint32_t gi = 0, row_n = 0;
+            const uint32_t idesc = IDESC_F16_M128 | IDESC_MN_MAJOR_AB | ((uint32_t)(f16 >> 3) << 17);  // N = live columns
+            RowEnt nxt = ent_at(0);
+            for (int k = 0; k < nslots; ++k) {
+                const RowEnt e = nxt;
+                nxt = ent_at(k + 1);
+                if (e.n <= 0) continue;
+                mbar_wait(bar_acc_empty, (row_n & 1u) ^ 1u);
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int base = 0; base < e.n; base += SUB, ++gi) {
+                    const int s = gi % NSTAGE;
+                    mbar_wait(bar_full(s), (gi / NSTAGE) & 1u);
+                    tc_fence_after();
+                    const int kc = (e.n - base) < SUB ? (e.n - base) : SUB;
+                    const int nk = (kc + 15) >> 4;
+                    const uint32_t tile = smem_base + OFF_STAGES + s * PAIR_BYTES;
+                    for (int kk = 0; kk < nk; ++kk) {   // 16 entries = two 8-entry K groups
+                        const uint32_t th = tile + kk * 2 * TILE_SBO, tl = th + TILE_BYTES;
+                        const uint64_t bh = umma_desc_mn(th, TILE_LBO, TILE_SBO), bl = umma_desc_mn(tl, TILE_LBO, TILE_SBO);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {   // matrix rows 128 h .. 128 h + 127 = feature blocks 2h, 2h + 1
+                            const uint64_t ah = umma_desc_mn(th + 2 * h * TILE_LBO, TILE_LBO, TILE_SBO);
+                            const uint64_t al = umma_desc_mn(tl + 2 * h * TILE_LBO, TILE_LBO, TILE_SBO);
+                            const uint32_t d = tmem_base + (uint32_t)(h * F);
+                            umma_f16(d, ah, bh, idesc, accumulate);  // zh zh^T
+                            umma_f16(d, ah, bl, idesc, 1u);          // zh zl^T
+                            umma_f16(d, al, bh, idesc, 1u);          // zl zh^T
+                        }
+                        accumulate = 1;
+                    }
+                    tc_commit(bar_empty(s));
+                }
+                tc_commit(bar_acc_full);
+                ++row_n;
+            }
+        }
+    } else {
+        // =============================== SOLVE (256 x 256 matrix resident in TMEM) ===============================
+        const int t = tid;                     // matrix row
+        const int hh = t >> 7;                 // matrix half = column base 256 hh
+        const int q = warp & 3;                // TMEM lane quarter this warp may access
+        const uint32_t tileH = smem_base + OFF_TILEH, tileL = smem_base + OFF_TILEL;
+        const uint32_t Nst = smem_base + OFF_NINV, zst = smem_base + OFF_ZB, Dblk = smem_base + OFF_DBLK, bfin = smem_base + OFF_BFIN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * F);
+        const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
+        uint32_t row_n = 0, panel_n = 0;
+        RowEnt nxt = ent_at(0);
+        for (int k = 0; k < nslots; ++k) {
+            const RowEnt e = nxt;
+            nxt = ent_at(k + 1);
+            if (e.n <= 0) continue;
+            const uint32_t rn = row_n++;
+            float* xout = p.X + (int64_t)e.row * p.ldx;
+            const float S = exp2f((float)e.sexp), inv_s = exp2f((float)-e.sexp), inv_s2 = inv_s * inv_s;
+            mbar_wait(bar_b_full, rn & 1u);
+            float bt;
+            {
+                const uint32_t bv = smem_base + OFF_BVEC + t * 4;
+                bt = (lds1(bv) + lds1(bv + F * 4)) + (lds1(bv + 2 * F * 4) + lds1(bv + 3 * F * 4));
+            }
+            mbar_arrive(bar_b_empty);
+            mbar_wait(bar_acc_full, rn & 1u);
+            tc_fence_after();
+            if (e.part >= 0) {
+                // ---- segment of a split row: park the partial; the last one to arrive sums them in segment order
+                const int4 sg = __ldg(segtab + e.part);  // split_id, nseg, first_part, seg
+                float* mine = parts + (size_t)(sg.z + sg.w) * PART_FLOATS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < f8; c0 += NB) {
+                    float a[NB];
+                    tmem_ld8(t_row + c0, a);
+                    float4* dst = reinterpret_cast<float4*>(mine + (c0 >> 3) * (F * NB) + t * NB);
+                    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+                    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+                }
+                mine[F * F + t] = bt;
+                __threadfence();
+                named_bar(1, SOLVERS);
+                if (t == 0) sts1(Dblk, __int_as_float(atomicAdd(counters + sg.x, 1) == sg.y - 1 ? 1 : 0));
+                named_bar(1, SOLVERS);
+                const bool last = __float_as_int(lds1(Dblk)) != 0;
+                named_bar(1, SOLVERS);
+                if (!last) {
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty);
+                    continue;
+                }
+                __threadfence();
+                const float* first = parts + (size_t)sg.z * PART_FLOATS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < f8; c0 += NB) {
+                    float a[NB] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int k2 = 0; k2 < sg.y; ++k2) {
+                        const float4* src = reinterpret_cast<const float4*>(first + (size_t)k2 * PART_FLOATS + (c0 >> 3) * (F * NB) + t * NB);
+                        const float4 x0 = __ldcg(src), x1 = __ldcg(src + 1);
+                        a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
+                        a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
+                    }
+                    tmem_st8(t_row + c0, a);
+                }
+                bt = 0.0f;
+                for (int k2 = 0; k2 < sg.y; ++k2) bt += __ldcg(first + (size_t)k2 * PART_FLOATS + F * F + t);
+                tc_fence_before();
+                named_bar(1, SOLVERS);
+                tc_fence_after();
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < f8; c0 += NB) {
+                if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
+                    mbar_wait(bar_panel, panel_n & 1u);
+                    ++panel_n;
+                    tc_fence_after();
+                }
+                float a[NB];
+                tmem_ld8(t_row + c0, a);
+                if (c0 + NB == f8) {  // last read of the accumulator: the Gram of the next row may start
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty);
+                }
+                const int rel = t - c0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, rel == i ? 1.0f : 0.0f);  // I + sum d y~ y~^T
+                const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
+                if (warp == (c0 >> 5)) {
+                    // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
+                    if (rel >= 0 && rel < NB) {
+                        sts4(Dblk + rel * 32, a[0], a[1], a[2], a[3]);
+                        sts4(Dblk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
+                        sts1(Dblk + 256 + rel * 4, bt);
+                    }
+                    __syncwarp();
+                    float d[36], bb[NB];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const float4 d0 = lds4(Dblk + i * 32);
+                        d[TRI(i, 0)] = d0.x;
+                        if (i >= 1) d[TRI(i, 1)] = d0.y;
+                        if (i >= 2) d[TRI(i, 2)] = d0.z;
+                        if (i >= 3) d[TRI(i, 3)] = d0.w;
+                        if (i >= 4) {
+                            const float4 d1 = lds4(Dblk + i * 32 + 16);
+                            d[TRI(i, 4)] = d1.x;
+                            if (i >= 5) d[TRI(i, 5)] = d1.y;
+                            if (i >= 6) d[TRI(i, 6)] = d1.z;
+                            if (i >= 7) d[TRI(i, 7)] = d1.w;
+                        }
+                    }
+                    {
+                        const float4 b0 = lds4(Dblk + 256), b1 = lds4(Dblk + 272);
+                        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+                        bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+                    }
+                    float ncol[NB], z[NB];
+                    const bool ok = factor8(d, bb, lane & 7, ncol, z);  // lane c holds column c of N = L^-1
+                    if (lane < NB) {
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) sts1(nd + i * 32 + lane * 4, S * ncol[i]);
+                    }
+                    if (lane == 0) {
+                        sts4(zd, inv_s * z[0], inv_s * z[1], inv_s * z[2], inv_s * z[3]);
+                        sts4(zd + 16, inv_s * z[4], inv_s * z[5], inv_s * z[6], inv_s * z[7]);
+                        if (!ok) {  // spectrum >= 1: only a numerical accident gets here; the LU kernel redoes the row
+                            atomicOr(flags, 2);
+                            p.fix_list[atomicAdd(p.fix_count, 1)] = e.row;
+                        }
+                    }
+                }
+                named_bar(1, SOLVERS);
+                float P[NB];
+                {
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const float4 n0 = lds4(nd + jj * 32);
+                        float v = a[0] * n0.x;
+                        if (jj >= 1) v = fmaf(a[1], n0.y, v);
+                        if (jj >= 2) v = fmaf(a[2], n0.z, v);
+                        if (jj >= 3) v = fmaf(a[3], n0.w, v);
+                        if (jj >= 4) {
+                            const float4 n1 = lds4(nd + jj * 32 + 16);
+                            v = fmaf(a[4], n1.x, v);
+                            if (jj >= 5) v = fmaf(a[5], n1.y, v);
+                            if (jj >= 6) v = fmaf(a[6], n1.z, v);
+                            if (jj >= 7) v = fmaf(a[7], n1.w, v);
+                        }
+                        P[jj] = v;
+                    }
+                    const bool pivot = rel >= 0 && rel < NB;
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) P[jj] = pivot ? 0.0f : P[jj];
+                    const float4 z0 = lds4(zd), z1 = lds4(zd + 16);
+                    float u0 = P[0] * z0.x, u1 = P[1] * z0.y;
+                    u0 = fmaf(P[2], z0.z, u0); u1 = fmaf(P[3], z0.w, u1);
+                    u0 = fmaf(P[4], z1.x, u0); u1 = fmaf(P[5], z1.y, u1);
+                    u0 = fmaf(P[6], z1.z, u0); u1 = fmaf(P[7], z1.w, u1);
+                    bt -= u0 + u1;
+                }
+                if (c0 + NB < f8) {
+                    float lh[NB], ll[NB];
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        lh[jj] = tf32_round(P[jj]);
+                        ll[jj] = P[jj] - lh[jj];
+                    }
+                    const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+                    sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
+                    sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
+                    sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
+                    sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
+                    fence_async_smem();
+                    tc_fence_before();
+                    named_bar(1, SOLVERS);
+                    if (t == 0) {
+                        // S[:, j] -= P P[j]^T for the live columns j >= c0 + 8, both matrix halves
+                        tc_fence_after();
+                        const uint32_t start = (uint32_t)((c0 + NB) >> 4) << 4;
+                        const uint32_t idesc = IDESC_TF32_NEG_M128 | ((((uint32_t)f16 - start) >> 3) << 17);
+                        const uint64_t bH = descH + (uint64_t)(start * 2), bL = descL + (uint64_t)(start * 2);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint64_t aH = descH + (uint64_t)(h * 128 * 2), aL = descL + (uint64_t)(h * 128 * 2);
+                            const uint32_t d = tmem_base + (uint32_t)(h * F) + start;
+                            umma_tf32(d, aH, bH, idesc, 1u);
+                            umma_tf32(d, aH, bL, idesc, 1u);
+                            umma_tf32(d, aL, bH, idesc, 1u);
+                        }
+                        tc_commit(bar_panel);
+                    }
+                }
+            }
+            // ---- block diagonal now: x_blk = N^T (N b_blk) ----
+            sts1(bfin + t * 4, bt);
+            named_bar(1, SOLVERS);
+            {
+                const int r8 = t & 7;
+                const uint32_t nb = Nst + (t >> 3) * 256, bq = bfin + (t >> 3) * 32;
+                const float4 b0 = lds4(bq), b1 = lds4(bq + 16);
+                const float bb[NB] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float xt = 0.0f;
+                if (t < f8) {
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        const float4 n0 = lds4(nb + jj * 32), n1 = lds4(nb + jj * 32 + 16);
+                        const float nr[NB] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                        float y = 0.0f;
+#pragma unroll
+                        for (int kk = 0; kk <= jj; ++kk) y = fmaf(nr[kk], bb[kk], y);
+                        float nsel = 0.0f;
+#pragma unroll
+                        for (int kk = 0; kk <= jj; ++kk) nsel = (kk == r8) ? nr[kk] : nsel;
+                        xt = fmaf(nsel, y, xt);
+                    }
+                }
+                xout[t] = t < f8 ? xt * inv_s2 : 0.0f;  // N was stored as S N; padding columns of the whitened solution are 0
+            }
+            named_bar(1, SOLVERS);  // Nst / bfin are rewritten by the next row
+        }
+    }
+    // =============================== TEARDOWN ===============================
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace p256
+
+size_t tc256_part_floats() { return p256::PART_FLOATS; }
+
+int tc256_launch(const HalfStepParams& p, const int4* tab, const int4* segtab, float* parts, int* counters,
+                 const uint32_t* hdr_u, int64_t extra_slot0, int* flags, int grid, cudaStream_t st) {
+    WMF_CUDA(cudaFuncSetAttribute(p256::als_half_step_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  p256::SMEM_BYTES));
+    p256::als_half_step_tc256_kernel<<<grid, p256::THREADS, p256::SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u,
+                                                                                   extra_slot0, flags);
+    WMF_LAUNCH_CHECK("als_half_step_tc256_kernel");
+    return WMF_OK;
+}
+
+}  // namespace wmf

@@ -86,6 +86,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
+// MN-major ("transposed") operand, 128-byte swizzle: 64 contiguous M/N elements per swizzle row, 8 K rows per
+// 1024-byte atom; LBO = bytes to the next 64 M/N elements, SBO = bytes to the next 8 K rows
+// (cute::UMMA make_umma_desc<Major::MN>, verified by scripts/probe/mma_mn_major_probe.cu)
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
 // K-major, no swizzle: 8-row x 16-byte core matrices; the two K-chunks of a row group are
 // LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart (panel operand, K = 8 fp32).
 __device__ __forceinline__ uint64_t umma_desc_panel(uint32_t smem_addr) {
@@ -95,6 +102,7 @@ __device__ __forceinline__ uint64_t umma_desc_panel(uint32_t smem_addr) {
 // cute::UMMA::InstrDescriptor: fp32 accumulate (bit 4), A/B formats at bits 7/10 (0 = F16, 2 = TF32),
 // bit 13 negates A, N >> 3 at bit 17, M >> 4 at bit 24; K-major A and B.
 constexpr uint32_t IDESC_F16_M128 = (1u << 4) | ((128u >> 4) << 24);                                            // N filled in at issue
+constexpr uint32_t IDESC_MN_MAJOR_AB = (1u << 15) | (1u << 16);                                                 // A and B MN-major
 constexpr uint32_t IDESC_TF32_NEG_M128 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((128u >> 4) << 24);  // N filled in at issue
 #define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
@@ -162,6 +170,9 @@ __device__ __forceinline__ void sts4(uint32_t a, float x, float y, float z, floa
 }
 __device__ __forceinline__ void sts4u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts2u(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void sts1(uint32_t a, float x) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");

@@ -194,15 +194,24 @@ class DeviceCSR:
 
     def transpose(self):
         """CSR of the transpose with ascending row ids inside every output row: the ordering
-        ``count_mat.T.tocsr()`` produces (wmf_model.py:128). One stable device sort by column."""
+        ``count_mat.T.tocsr()`` produces (wmf_model.py:128). The library's stable radix sort by column
+        (wmf_csr_transpose); unsorted or duplicated input entries are fine."""
+        lib = _lib.load()
         rows, cols = self.shape
-        perm = torch.sort(self.indices, stable=True).indices
-        out_indices = self.row_ids()[perm]
-        out_data = self.data[perm]
-        counts = torch.bincount(self.indices, minlength=cols)
-        out_indptr = torch.zeros(cols + 1, dtype=torch.int64, device=self.device)
-        torch.cumsum(counts, 0, out=out_indptr[1:])
-        return DeviceCSR(out_indptr, out_indices.contiguous(), out_data.contiguous(), (cols, rows))
+        dev = self.device
+        out_indptr = torch.empty(cols + 1, dtype=torch.int64, device=dev)
+        out_indices = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+        out_data = torch.empty(self.nnz, dtype=torch.float32, device=dev)
+        ws = workspace(lib.wmf_csr_transpose_workspace_bytes(rows, cols, self.nnz), dev)
+        with _on(dev):
+            _lib.check(lib.wmf_csr_transpose(_ptr(self.indptr), _ptr(self.indices), _ptr(self.data), rows, cols, self.nnz,
+                                             _ptr(out_indptr), _ptr(out_indices), _ptr(out_data), _ptr(ws), ws.numel(),
+                                             _stream(dev)), "wmf_csr_transpose")
+        return DeviceCSR(out_indptr, out_indices, out_data, (cols, rows))
+
+    def canonical(self):
+        """The same matrix with sorted column indices inside every row (two transposes)."""
+        return self.transpose().transpose()
 
     def row_slice(self, r0, r1):
         """Rows [r0, r1) as an independent DeviceCSR (used to shard rows across GPUs)."""

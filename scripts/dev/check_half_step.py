@@ -20,6 +20,8 @@ CASES = {
     "f129b": (1500, 1200, 90_000, 129, True),
     "f256": (1500, 1200, 60_000, 256, False),
     "f16": (500, 300, 9_000, 16, False),
+    "f192": (1500, 1200, 120_000, 192, False),
+    "f256_long": (600, 30_000, 400_000, 256, False),   # long rows: segments of the 256-wide kernel
 }
 
 

@@ -118,13 +118,43 @@ def test_gram_block_partials_reproduce_gram(cuda_device, n, f, ones):
     np.testing.assert_array_equal(G, G.T)
 
 
-def test_transpose_matches_scipy(cuda_device):
-    C = make_counts(700, 450, 20_000, seed=21)
+@pytest.mark.parametrize("rows,cols,nnz", [(700, 450, 20_000), (3, 70_000, 5_000), (5000, 1, 800), (6040, 3706, 1_000_000),
+                                           (40, 300_000, 90_000)])
+def test_transpose_matches_scipy(cuda_device, rows, cols, nnz):
+    """N1: the library's stable radix sort by column reproduces count_mat.T.tocsr() (wmf_model.py:128) exactly:
+    row pointer, ascending row ids inside every output row, values."""
+    C = make_counts(rows, cols, nnz, seed=21)
     CT = DeviceCSR.from_scipy(C, cuda_device).transpose().to_scipy()
     ref = C.T.tocsr()
     np.testing.assert_array_equal(CT.indptr, ref.indptr)
     np.testing.assert_array_equal(CT.indices, ref.indices)
     np.testing.assert_array_equal(CT.data, ref.data)
+
+
+def test_transpose_unsorted_duplicates_and_canonical(cuda_device):
+    """Unsorted column order inside rows, duplicate (row, column) entries and empty rows: the transpose keeps every
+    entry (SciPy does not sum duplicates either) in CSR traversal order; two transposes give sorted indices."""
+    rng = np.random.default_rng(4)
+    rows, cols = 300, 200
+    lens = rng.integers(0, 40, rows)
+    lens[[3, 77]] = 0
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    indices = np.concatenate([rng.integers(0, cols, n) for n in lens]).astype(np.int32)   # unsorted, with repeats
+    data = rng.random(indptr[-1]).astype(np.float32)
+    C = scipy.sparse.csr_matrix((data, indices, indptr), shape=(rows, cols))
+    Cd = DeviceCSR(dev(indptr.astype(np.int64), cuda_device), dev(indices, cuda_device), dev(data, cuda_device), (rows, cols))
+    CT = Cd.transpose().to_scipy()
+    ref = C.T.tocsr()   # csc -> csr: counting sort in traversal order, duplicates kept
+    np.testing.assert_array_equal(CT.indptr, ref.indptr)
+    np.testing.assert_array_equal(CT.indices, ref.indices)
+    np.testing.assert_array_equal(CT.data, ref.data)
+    canon = Cd.canonical().to_scipy()
+    assert canon.shape == C.shape and canon.nnz == C.nnz
+    assert all(np.all(np.diff(canon.indices[canon.indptr[r]:canon.indptr[r + 1]]) >= 0) for r in range(rows))
+    assert abs(canon - C).max() < 1e-6
+    empty = DeviceCSR(torch.zeros(6, dtype=torch.int64, device=cuda_device), torch.empty(0, dtype=torch.int32, device=cuda_device),
+                      torch.empty(0, dtype=torch.float32, device=cuda_device), (5, 9)).transpose()
+    assert empty.shape == (9, 5) and int(empty.indptr.abs().sum()) == 0
 
 
 # ------------------------------------------------------------------------------- K2
@@ -641,10 +671,8 @@ def test_half_step_dual_rows_every_length(cuda_device, f, bias):
         assert np.all(X[np.array(lens) == 0] == 0) and np.all(np.isfinite(X))
         check_half_step(f"dual_rows/f{f}{'b' if bias else ''}/{kind}", "tcgen05", X, step(Y, C, 0.1), step(Y, C, 0.1, np.float64))
         assert (flags & 2) == 0
-        if f <= 128:                   # only a negative weight needs the CUDA-core kernel: with biases the stored
-            assert fixed == (1 if bias else 0)   # zero becomes 0 - beta < 0
-        else:                          # above 128 features the rows longer than dual_max (and the zero-weight row) do
-            assert fixed == sum(1 for n in lens if n > nd) + 1
+        # only a negative weight needs the CUDA-core kernel: with biases the stored zero becomes 0 - beta < 0
+        assert fixed == (1 if bias else 0)
         X2, _ = run_half_step(Y, C, bias, _lib.ALGO_TCGEN05, cuda_device, use_row_order=False)
         np.testing.assert_array_equal(X, X2)
         Xa, _ = run_half_step(Y, C[:40], bias, _lib.ALGO_TCGEN05, cuda_device)   # row sharding never changes a row's bits
