@@ -36,7 +36,10 @@ constexpr int TILE_BYTES = 128 * 128; // 128 entries x 64 fp16 features
 constexpr int PAIR_BYTES = 2 * TILE_BYTES;
 constexpr int NB = 8;
 constexpr int NGROUP = 4, GROUP = 128;
-constexpr int NGATHER = 8;            // gather warps
+#ifndef WMF_DUAL_NGATHER
+#define WMF_DUAL_NGATHER 8
+#endif
+constexpr int NGATHER = WMF_DUAL_NGATHER;   // gather warps
 constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WARP0 + NGATHER;
 constexpr int THREADS = (MMA_WARP + 1) * 32;  // 800
 constexpr uint32_t TMEM_COLS = 512;
@@ -131,11 +134,11 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
             if (e.n <= 0) continue;
             const int n = e.n, n16 = (n + 15) & ~15;
             const float S = exp2f((float)e.sexp);
-            // this warp's entries j = w, w + 8, ...: lane l holds entry w + 8 l
+            // this warp's entries j = w, w + NGATHER, ...: lane l holds entry w + NGATHER l
             int my_idx = -1;
             float my_s = 0.0f;
             {
-                const int j = w + 8 * lane;
+                const int j = w + NGATHER * lane;
                 if (j < n) {
                     my_idx = __ldg(p.indices + e.lo + j);
                     float d = __ldg(p.data + e.lo + j);
@@ -143,7 +146,7 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                     my_s = S * sqrtf(d);
                 }
             }
-            const int cnt = (n16 - w + 7) >> 3;     // entries (padding rows included) this warp writes
+            const int cnt = (n16 - w + NGATHER - 1) / NGATHER;     // entries (padding rows included) this warp writes
             uint32_t sbase[2];                      // stage of this lane's chunk, per pass
 #pragma unroll
             for (int ps = 0; ps < 2; ++ps) {
@@ -173,7 +176,7 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     if (idxs[b] == -2) continue;
-                    const uint32_t j = (uint32_t)(w + 8 * (e0 + b));
+                    const uint32_t j = (uint32_t)(w + NGATHER * (e0 + b));
                     const uint32_t roff = (j >> 3) * 1024u + (j & 7u) * 128u + (((q ^ (j & 7u))) << 4) + half8;
 #pragma unroll
                     for (int ps = 0; ps < 2; ++ps) {
@@ -265,15 +268,17 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
             }
             mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
             tc_fence_after();
+            // a warp whose 32 lanes lie beyond the padded system (n <= 32: three of the four) owns no matrix row: it
+            // only keeps the group's barriers (and, if it is warp g, the pivot factor) and skips the per-row work
+            const bool active = qw * 32 < n16;
 #pragma unroll 1
             for (int c0 = 0; c0 < n8; c0 += NB) {
                 if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
-                    mbar_wait(bar_panel(g), panel_n & 1u);
+                    if (active) { mbar_wait(bar_panel(g), panel_n & 1u); tc_fence_after(); }
                     ++panel_n;
-                    tc_fence_after();
                 }
-                float a[NB];
-                tmem_ld8(t_row + c0, a);
+                float a[NB] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (active) tmem_ld8(t_row + c0, a);
                 if (c0 + NB == n8) {  // last read of the accumulator: the Gram of this group's next row may start
                     tc_fence_before();
                     mbar_arrive(bar_acc_empty(g));
@@ -341,8 +346,8 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                     }
                 }
                 named_bar(bar_id, GROUP);
-                float P[NB];
-                {
+                float P[NB] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (active) {
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
                         const float4 n0 = lds4(nd + jj * 32);
@@ -372,19 +377,21 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                     bt -= u0 + u1;
                 }
                 if (c0 + NB < n8) {
-                    float lh[NB], ll[NB];
+                    if (active) {
+                        float lh[NB], ll[NB];
 #pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        lh[jj] = tf32_round(P[jj]);
-                        ll[jj] = P[jj] - lh[jj];
+                        for (int jj = 0; jj < NB; ++jj) {
+                            lh[jj] = tf32_round(P[jj]);
+                            ll[jj] = P[jj] - lh[jj];
+                        }
+                        const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+                        sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
+                        sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
+                        sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
+                        sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
+                        fence_async_smem();
+                        tc_fence_before();
                     }
-                    const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
-                    sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
-                    sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
-                    sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
-                    sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
-                    fence_async_smem();
-                    tc_fence_before();
                     named_bar(bar_id, GROUP);
                     if (t == ISSUE_T) {
                         tc_fence_after();

@@ -602,6 +602,9 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * F);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
         const int f8 = p.f8, f16 = p.f16;  // live width: the whitened system is the identity beyond it
+        // a warp whose 32 lanes lie beyond the live width (f <= 64: two of the four) owns no matrix row: it only keeps
+        // the group's barriers (and, if it is warp g, the pivot factor) and skips the per-row work
+        const bool active = q * 32 < f16;
         uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
@@ -679,13 +682,12 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
             for (int c0 = 0; c0 < f8; c0 += NB) {
                 if (prof) t3 = clock64();
                 if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
-                    mbar_wait(bar_panel(g), panel_n & 1u);
+                    if (active) { mbar_wait(bar_panel(g), panel_n & 1u); tc_fence_after(); }
                     ++panel_n;
-                    tc_fence_after();
                 }
                 if (prof) { t4 = clock64(); ph_wait += t4 - t3; }
-                float a[NB];
-                tmem_ld8(t_row + c0, a);
+                float a[NB] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (active) tmem_ld8(t_row + c0, a);
                 if (c0 + NB == f8) {  // last read of the accumulator: the Gram of this group's next row may start
                     tc_fence_before();
                     mbar_arrive(bar_acc_empty(g));
@@ -759,8 +761,8 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 named_bar(bar_id, GROUP);
                 // ---- every row outside the block: P = a (S N)^T = S a N^T, rhs -= P (zb / S); the block's own rows
                 // are pivots (P = 0) ----
-                float P[NB];
-                {
+                float P[NB] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (active) {
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) {
                         const float4 n0 = lds4(nd + jj * 32);
@@ -790,19 +792,21 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                     bt -= u0 + u1;
                 }
                 if (c0 + NB < f8) {
-                    float lh[NB], ll[NB];
+                    if (active) {
+                        float lh[NB], ll[NB];
 #pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
-                        lh[jj] = tf32_round(P[jj]);
-                        ll[jj] = P[jj] - lh[jj];  // exact; the tensor core reads its top 19 bits (error 2^-23 of P)
+                        for (int jj = 0; jj < NB; ++jj) {  // the accumulator holds S^2 W: the update is (S P)(S P)^T
+                            lh[jj] = tf32_round(P[jj]);
+                            ll[jj] = P[jj] - lh[jj];  // exact; the tensor core reads its top 19 bits (error 2^-23 of P)
+                        }
+                        const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+                        sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
+                        sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
+                        sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
+                        sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
+                        fence_async_smem();
+                        tc_fence_before();
                     }
-                    const uint32_t o = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
-                    sts4(tileH + o, lh[0], lh[1], lh[2], lh[3]);
-                    sts4(tileH + o + 128, lh[4], lh[5], lh[6], lh[7]);
-                    sts4(tileL + o, ll[0], ll[1], ll[2], ll[3]);
-                    sts4(tileL + o + 128, ll[4], ll[5], ll[6], ll[7]);
-                    fence_async_smem();
-                    tc_fence_before();
                     if (prof) t3 = clock64();
                     named_bar(bar_id, GROUP);
                     if (t == ISSUE_T) {
@@ -960,7 +964,9 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
     p.f16 = (in.f + 15) / 16 * 16;
     p.fix_list = reinterpret_cast<int*>(base + L.off_fix);
     p.fix_count = reinterpret_cast<int*>(hdr_u + 8);
-    p.nd_max = dual_enabled() ? tc_dual_max_entries() : 0;
+    // wider than 128 features one row at a time fits the tensor memory of an SM (half_step_tc256.cu): the dual kernel
+    // (four n x n systems in flight) takes everything it can hold, n <= 128
+    p.nd_max = dual_enabled() ? (FP > F ? 128 : tc_dual_max_entries()) : 0;
     p.prof = profile_enabled() ? reinterpret_cast<long long*>(base + WS_PROF) : nullptr;
     const int primal_ok = 1;   // 128-wide kernel of this file, or the 256-wide one (half_step_tc256.cu)
     tc_prep_rows_kernel<<<(unsigned)((in.sched_len + 7) / 8), 256, 0, st>>>(p, tab, segtab, dtab, hdr_u, extra_slot0,
