@@ -21,88 +21,169 @@ namespace wmf {
 
 namespace {
 
-constexpr int CW_THREADS = 256;   // one thread per matrix row / column (f <= 256)
+constexpr int CW_THREADS = 512;    // 16 warps: warp ty owns the rows ty, ty + 16, ty + 32, ... of the matrix, lane tx the columns tx + 32 b
+constexpr int CW_NB = 8;           // panel width
 
-// A (double, ld) holds L in its lower triangle (diagonal included) and, after the second phase, column j of
-// L^-1 below the diagonal in ROW j of the strict upper triangle; 1 / L_jj in dinv.
-// The work is ~f^3/2 double FMAs (nothing); the cost is the chain of f dependent columns, so every phase is
-// written for latency: thread i owns row i (Cholesky, two barriers per column, four accumulators per dot product),
-// thread j owns column j of L^-1 (forward substitution, no barrier at all: it only reads L and its own column).
+// Cholesky of an 8 x 8 block (lower triangle d, packed rows) and, in place, the inverse of its factor, in double,
+// straight line: every lane of the calling warp computes all of it (the chain of dependent operations is what costs).
+#define T8(i, j) ((i) * ((i) + 1) / 2 + (j))
+__device__ __forceinline__ bool chol8_inv(double (&d)[36]) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double p = d[T8(k, k)];
+        if (!(p > 0.0)) { ok = false; p = 1.0; }
+        const double r = rsqrt(p);
+        d[T8(k, k)] = r;   // 1 / L_kk (the inversion below wants the reciprocal)
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) d[T8(i, k)] *= r;
+#pragma unroll
+        for (int j = k + 1; j < 8; ++j)
+#pragma unroll
+            for (int i = j; i < 8; ++i) d[T8(i, j)] = fma(-d[T8(i, k)], d[T8(j, k)], d[T8(i, j)]);
+    }
+    // in-place inverse of the lower-triangular factor, last column first (LAPACK trti2): the trailing block is
+    // already inverted when column j is formed: x <- -(1 / L_jj) T x
+#pragma unroll
+    for (int j = 6; j >= 0; --j) {
+#pragma unroll
+        for (int i = 7; i > j; --i) {   // descending i: x_k (k < i) is still the old column
+            double acc = 0.0;
+#pragma unroll
+            for (int k = j + 1; k < i; ++k) acc = fma(d[T8(i, k)], d[T8(k, j)], acc);
+            acc = fma(d[T8(i, i)], d[T8(i, j)], acc);   // T_ii = 1 / L_ii
+            d[T8(i, j)] = -acc * d[T8(j, j)];
+        }
+    }
+    return ok;
+}
+
+// L = chol(G) and Z = L^-1 in ONE right-looking sweep over 8-column panels, in double, in a single lower-triangular
+// array M (columns left of the current panel already hold Z, columns from the panel on hold the trailing matrix):
+//   N  = inverse of the Cholesky factor of the 8 x 8 pivot block
+//   l_i = M[i][panel] N^T for the rows below (the panel of L, needed by this step only)
+//   pivot rows:  Z[p][j] <- N Z[p][j] (j left of the panel),  Z[p][panel] = N
+//   rows below:  M[i][j] -= l_i . R[:, j]  for j <= i, with R = [N Z[p] | N | l^T]  (Z part, new Z columns, trailing matrix)
+// Every step is a rank-8 update of the whole triangle: no separate triangular inversion, f / 8 steps of three
+// barriers each. One CTA; the work is ~f^3 / 2 double FMAs (nothing), the cost is the chain of f / 8 panel steps.
 __global__ void __launch_bounds__(CW_THREADS, 1)
 chol_whiten_kernel(const float* __restrict__ G, int f, int FP, double* __restrict__ gscratch, int use_smem,
                    float* __restrict__ Mw, float* __restrict__ Mu, float* __restrict__ eye, int* __restrict__ flags) {
     extern __shared__ double cw_smem[];
-    __shared__ double s_rpiv;
+    __shared__ double Nsh[36];
     __shared__ int s_bad;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+    const int FPAD = (f + CW_NB - 1) / CW_NB * CW_NB;
+    const int ld = FPAD | 1;  // odd leading dimension: row-strided accesses spread over the banks
+    double* M = use_smem ? cw_smem : gscratch;
+    double* R = M + (size_t)FPAD * ld;          // [8][FPAD]
     if (tid == 0) s_bad = 0;
-    const int ld = f | 1;  // odd leading dimension: row-strided accesses spread over the banks
-    double* A = use_smem ? cw_smem : gscratch;
-    double* dinv = A + (size_t)f * ld;
-    for (int e = tid; e < f * f; e += CW_THREADS) {
-        const int i = e / f, j = e % f;
-        if (j <= i) A[i * ld + j] = (double)G[(size_t)i * f + j];
+    for (int e = tid; e < FPAD * FPAD; e += CW_THREADS) {
+        const int i = e / FPAD, j = e % FPAD;
+        if (j <= i) M[(size_t)i * ld + j] = (i < f) ? (double)G[(size_t)i * f + j] : (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
-    // ---- left-looking Cholesky: column k from the k columns before it
-    const int i = tid;
-    const double* ai = A + (size_t)(i < f ? i : 0) * ld;
-    for (int k = 0; k < f; ++k) {
-        double s = 0.0;
-        if (i >= k && i < f) {
-            const double* ak = A + (size_t)k * ld;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int j = 0;
-            for (; j + 4 <= k; j += 4) {
-                a0 = fma(ai[j], ak[j], a0);
-                a1 = fma(ai[j + 1], ak[j + 1], a1);
-                a2 = fma(ai[j + 2], ak[j + 2], a2);
-                a3 = fma(ai[j + 3], ak[j + 3], a3);
-            }
-            for (; j < k; ++j) a0 = fma(ai[j], ak[j], a0);
-            s = ai[k] - ((a0 + a1) + (a2 + a3));
-            if (i == k) {
-                if (!(s > 0.0)) { s_bad = 1; s = 1.0; }  // G is not positive definite
-                const double r = rsqrt(s);
-                s_rpiv = r;           // L_kk = s * r = sqrt(s) falls out of the common store below
-                dinv[k] = r;          // 1 / L_kk
+    for (int k0 = 0; k0 < FPAD; k0 += CW_NB) {
+        // ---- A: pivot block (warp 0, every lane the same straight-line code)
+        if (ty == 0) {
+            double d[36];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) d[T8(i, j)] = M[(size_t)(k0 + i) * ld + k0 + j];
+            const bool ok = chol8_inv(d);
+            if (tx == 0) {
+#pragma unroll
+                for (int q = 0; q < 36; ++q) Nsh[q] = d[q];
+                if (!ok) s_bad = 1;
             }
         }
         __syncthreads();
-        if (i >= k && i < f) A[(size_t)i * ld + k] = s * s_rpiv;
+        // ---- B: thread j builds column j of R and rewrites the pivot rows
+        if (tid < FPAD) {
+            const int j = tid;
+            double nn[36];
+#pragma unroll
+            for (int q = 0; q < 36; ++q) nn[q] = Nsh[q];
+            if (j < k0) {                     // R[:, j] = N Z[pivot rows][j]
+                double z[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) z[c] = M[(size_t)(k0 + c) * ld + j];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c2 = 0; c2 <= c; ++c2) acc = fma(nn[T8(c, c2)], z[c2], acc);
+                    R[(size_t)c * FPAD + j] = acc;
+                    M[(size_t)(k0 + c) * ld + j] = acc;
+                }
+            } else if (j < k0 + CW_NB) {      // R[:, panel] = N (lower), which is also the pivot block of Z
+                const int c2 = j - k0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v = (q == c2 && q <= c) ? nn[T8(c, q)] : v;
+                    R[(size_t)c * FPAD + j] = v;
+                    if (c2 <= c) M[(size_t)(k0 + c) * ld + j] = v;
+                }
+            } else {                          // R[:, j] = l_j = N M[j][panel] (the row of the L panel)
+                double m[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) m[c] = M[(size_t)j * ld + k0 + c];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int c2 = 0; c2 <= c; ++c2) acc = fma(nn[T8(c, c2)], m[c2], acc);
+                    R[(size_t)c * FPAD + j] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- C: rows below the panel: M[i][j] -= l_i . R[:, j] for j <= i (panel columns start from zero)
+        for (int i0 = ty; i0 < FPAD; i0 += 32) {     // two rows per pass share the loads of R
+            const int i1 = i0 + 16;
+            const bool on0 = i0 >= k0 + CW_NB, on1 = i1 >= k0 + CW_NB && i1 < FPAD;
+            if (!on0 && !on1) continue;              // warp-uniform
+            double l0[8], l1[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                l0[c] = on0 ? R[(size_t)c * FPAD + i0] : 0.0;
+                l1[c] = on1 ? R[(size_t)c * FPAD + i1] : 0.0;
+            }
+            const int jmax = on1 ? i1 : i0;
+            for (int j = tx; j <= jmax; j += 32) {
+                double r[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) r[c] = R[(size_t)c * FPAD + j];
+                const bool panel = j >= k0 && j < k0 + CW_NB;
+                if (on0 && j <= i0) {
+                    double m = panel ? 0.0 : M[(size_t)i0 * ld + j];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) m = fma(-l0[c], r[c], m);
+                    M[(size_t)i0 * ld + j] = m;
+                }
+                if (on1 && j <= i1) {
+                    double m = panel ? 0.0 : M[(size_t)i1 * ld + j];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) m = fma(-l1[c], r[c], m);
+                    M[(size_t)i1 * ld + j] = m;
+                }
+            }
+        }
         __syncthreads();
     }
-    // ---- L^-1 column by column (forward substitution): z_j = 1/L_jj, z_i = -(sum_{j<=k<i} L_ik z_k) / L_ii
-    if (tid < f) {
-        const int j = tid;
-        double* zrow = A + (size_t)j * ld;   // z_i (i > j) lives at A[j][i]
-        const double zj = dinv[j];
-        for (int r = j + 1; r < f; ++r) {
-            const double* ar = A + (size_t)r * ld;
-            double a0 = ar[j] * zj, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int k = j + 1;
-            for (; k + 4 <= r; k += 4) {
-                a0 = fma(ar[k], zrow[k], a0);
-                a1 = fma(ar[k + 1], zrow[k + 1], a1);
-                a2 = fma(ar[k + 2], zrow[k + 2], a2);
-                a3 = fma(ar[k + 3], zrow[k + 3], a3);
-            }
-            for (; k < r; ++k) a0 = fma(ar[k], zrow[k], a0);
-            zrow[r] = -((a0 + a1) + (a2 + a3)) * dinv[r];
-        }
-    }
-    __syncthreads();
     // ---- multipliers, zero padded to FP x FP (zero matrices when G is not positive definite: every row
-    // then goes to the LU fix-up list, see tc_prep_rows_kernel)
+    // then goes to the LU fix-up list, see tc_prep_rows_kernel). M's lower triangle is Z = L^-1.
     const bool bad = s_bad != 0;
     if (bad && tid == 0) atomicOr(flags, 8);
     for (int e = tid; e < FP * FP; e += CW_THREADS) {
         const int k = e / FP, n = e % FP;
         float w = 0.0f, u = 0.0f;
         if (!bad && k < f && n < f) {
-            if (n > k) w = (float)A[(size_t)k * ld + n];        // Linv[n][k], n > k
-            else if (n == k) w = u = (float)dinv[k];
-            else u = (float)A[(size_t)n * ld + k];              // Linv[k][n], k > n
+            if (n >= k) w = (float)M[(size_t)n * ld + k];   // Linv[n][k]
+            if (k >= n) u = (float)M[(size_t)k * ld + n];   // Linv[k][n]
         }
         Mw[e] = w;
         Mu[e] = u;
@@ -209,12 +290,17 @@ rmul_kernel(const float* __restrict__ in, int64_t rows, int64_t ldin, int kin, i
 
 }  // namespace
 
-size_t whiten_scratch_bytes(int f) {  // double f x (f|1) + f, used when the matrix does not fit shared memory
-    return align_up(((size_t)f * (f | 1) + f) * sizeof(double), 256);
+static size_t chol_doubles(int f) {   // triangular array (square storage, odd ld) + the 8-row panel R
+    const size_t FPAD = (size_t)(f + CW_NB - 1) / CW_NB * CW_NB;
+    return FPAD * (FPAD | 1) + CW_NB * FPAD;
+}
+
+size_t whiten_scratch_bytes(int f) {  // only touched when the matrix does not fit shared memory (f > ~160)
+    return align_up(chol_doubles(f) * sizeof(double), 256);
 }
 
 int chol_whiten(const float* G, int f, int FP, void* scratch, float* Mw, float* Mu, float* eye, int* flags, cudaStream_t st) {
-    const size_t need = ((size_t)f * (f | 1) + f) * sizeof(double);
+    const size_t need = chol_doubles(f) * sizeof(double);
     const int use_smem = need <= 200 * 1024 ? 1 : 0;
     if (use_smem)
         WMF_CUDA(cudaFuncSetAttribute(chol_whiten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
