@@ -5,6 +5,8 @@ Nothing in this module computes on the host or with torch operators on the hot p
 used for allocation, H2D/D2H copies, the current stream, and (in ``DeviceCSR.transpose``) a
 stable device sort for the one-off CSR transpose.
 """
+import weakref
+
 import numpy as np
 import torch
 
@@ -123,39 +125,6 @@ class DeviceCSR:
         indices = _h2d(mat.indices, np.int32, device)
         data = _h2d(mat.data, np.float32, device)
         return cls(indptr, indices, data, mat.shape)
-
-    @classmethod
-    def from_scipy_sharded(cls, mat, device, bounds, group=None):
-        """The full matrix on every rank of a row-sharded run, but only this rank's rows
-        [bounds[rank], bounds[rank+1]) cross PCIe: the index / value slices are all-gathered between the
-        GPUs (NVLink), which replaces world x nnz x 8 bytes of host traffic by nnz x 8."""
-        import torch.distributed as dist
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-        mat = mat.tocsr()
-        if mat.shape[1] >= 2 ** 31:
-            raise ValueError("column count must fit int32")
-        ip = np.asarray(mat.indptr, dtype=np.int64)
-        offs = ip[np.asarray(bounds, dtype=np.int64)]
-        sizes = np.diff(offs)
-        mx = int(sizes.max()) if len(sizes) else 0
-        lo, hi = int(offs[rank]), int(offs[rank + 1])
-        indptr = _h2d(ip, np.int64, device)
-        nnz = int(ip[-1])
-        if mx == 0:
-            return cls(indptr, torch.empty(0, dtype=torch.int32, device=device),
-                       torch.empty(0, dtype=torch.float32, device=device), mat.shape)
-        out = []
-        for host, dtype, tdtype in ((mat.indices, np.int32, torch.int32), (mat.data, np.float32, torch.float32)):
-            send = torch.zeros(mx, dtype=tdtype, device=device)
-            if hi > lo:
-                send[:hi - lo] = _h2d(host[lo:hi], dtype, device)
-            recv = torch.empty(world * mx, dtype=tdtype, device=device)
-            dist.all_gather_into_tensor(recv, send, group=group)
-            full = torch.empty(nnz, dtype=tdtype, device=device)
-            for g in range(world):
-                full[int(offs[g]):int(offs[g + 1])] = recv[g * mx:g * mx + int(sizes[g])]
-            out.append(full)
-        return cls(indptr, out[0], out[1], mat.shape)
 
     @property
     def device(self):
@@ -413,7 +382,7 @@ def half_step(csr, Y, G, bias=False, algo=_lib.ALGO_AUTO, out=None, use_row_orde
                                          _ptr(order), 0 if order is None else order.numel(), _ptr(Y), Y.stride(0), f,
                                          _ptr(G), int(bool(bias)), _ptr(X), X.stride(0), int(algo), _ptr(ws), ws.numel(),
                                          _stream(Y.device)), "wmf_als_half_step")
-    half_step.last_ws = ws
+    half_step.last_ws = weakref.ref(ws)
     return X
 
 
@@ -421,7 +390,9 @@ def half_step_status(ws=None):
     """(flags, fix-up rows) of the last tcgen05 half-step that used ``ws`` (synchronises its stream)."""
     import ctypes
     lib = _lib.load()
-    ws = ws if ws is not None else getattr(half_step, "last_ws", None)
+    if ws is None:
+        ref = getattr(half_step, "last_ws", None)
+        ws = ref() if ref is not None else None
     if ws is None:
         return 0, 0
     flags, fixed = ctypes.c_int(0), ctypes.c_int(0)

@@ -22,7 +22,8 @@ from . import _lib, engine, sharding
 
 
 class ResidentEpoch:
-    def __init__(self, C, CT, items0, gamma, bias=False, algo=_lib.ALGO_AUTO, ub=None, ib=None, graphs=True, peer=True):
+    def __init__(self, C, CT, items0, gamma, bias=False, algo=_lib.ALGO_AUTO, ub=None, ib=None, graphs=True, peer=True,
+                 count_launches=True):
         """C / CT: this rank's row slices (DeviceCSR) of the count matrix and of its transpose; ub / ib: shard
         boundaries (None on one GPU); items0: full initial item factors on the device; peer: exchange over peer
         memory when it is available (else NCCL)."""
@@ -34,7 +35,7 @@ class ResidentEpoch:
         n_users = C.shape[0] if ub is None else int(ub[-1])
         n_items = CT.shape[0] if ib is None else int(ib[-1])
         self.n_users, self.n_items = n_users, n_items
-        self.px = sharding.PeerBuffers.create(n_users, n_items, f, dev) if (self.world > 1 and peer) else None
+        self.px = sharding.PeerBuffers.cached(n_users, n_items, f, dev) if (self.world > 1 and peer) else None
         if self.px is not None:
             self.items, self.users = self.px.views["items"], self.px.views["users"]
             self.items.copy_(items0)
@@ -65,11 +66,13 @@ class ResidentEpoch:
         self.graphs = None
         self.launches_per_epoch = 0
         if self.px is not None:
+            # every rank's initial items / zeroed users are in place (and nobody still reads the buffers of an earlier
+            # epoch object) before anyone pushes
             torch.cuda.synchronize(dev)
-            self.px.barrier()     # every rank's initial items / zeroed users are in place before anyone pushes
+            self.px.barrier()
         if graphs:
             self._capture()
-        else:
+        elif count_launches:
             self._count_launches()
 
     # ---- the four stages (eager form; captured verbatim)

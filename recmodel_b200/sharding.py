@@ -102,6 +102,17 @@ class PeerBuffers:
     def __init__(self, handle, flat, views, table, rank, world):
         self.handle, self.flat, self.views, self.table, self.rank, self.world = handle, flat, views, table, rank, world
 
+    _cache = {}
+
+    @classmethod
+    def cached(cls, n_users, n_items, f, device, group=None):
+        """``create`` once per (shape, device): the rendezvous (IPC handle exchange) costs milliseconds and the
+        buffers can be reused by consecutive trainings of the same shape."""
+        key = (int(n_users), int(n_items), int(f), str(device), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls.create(n_users, n_items, f, device, group)
+        return cls._cache[key]
+
     @classmethod
     def create(cls, n_users, n_items, f, device, group=None):
         from . import engine

@@ -189,19 +189,16 @@ class WMF(RecModel):
                 raise AttributeError("'NoneType' object has no attribute 'data' (weighted training needs count_mat)")
             if pre_process_count not in ("log", "linear"):
                 raise ValueError(f"Pre_process_count {pre_process_count} is not implement please use log or linear.")
-            ub = None
-            if world > 1:  # every rank uploads its own rows only; the slices are all-gathered over NVLink
-                count_mat = count_mat.tocsr()
-                f_cost = self.dim + (1 if self.bias is True else 0)
-                ub = sharding.balanced_row_partition(np.diff(count_mat.indptr), world, f_cost,
-                                                     align=engine.gram_block_rows(count_mat.shape[0]))
-                C_full = DeviceCSR.from_scipy_sharded(count_mat, dev, ub)
-            else:
-                C_full = DeviceCSR.from_scipy(count_mat, dev)
+            # Row-sharded runs: every rank uploads the whole matrix over its own PCIe link (in parallel, so no slower
+            # than one GPU) and builds the transpose locally; only the epoch itself is sharded. Exchanging slices of
+            # the matrix between the GPUs instead cost more than it saved (31 ms against 22 ms at 2 GPUs, round 1).
+            C_full = DeviceCSR.from_scipy(count_mat, dev)
+            stats["host_marks_ms"] = [("upload issued", (time.perf_counter() - t_start) * 1e3)]
             C_full = C_full.with_data(engine.preprocess_(C_full.data, pre_process_count, alpha, beta))
             CT_full = C_full.transpose()  # count_mat.T.tocsr()  (:128)
+            stats["host_marks_ms"].append(("transpose issued", (time.perf_counter() - t_start) * 1e3))
             it = self._train_weighted(C_full, CT_full, util_d, iterations, verbose, eval_mat, cores, stopping_rounds,
-                                      min_improvement, stats, rank_id, world, ub)
+                                      min_improvement, stats, rank_id, world)
         torch.cuda.synchronize(dev)
         stats["total_ms"] = (time.perf_counter() - t_start) * 1e3
         self.last_train_stats = stats
@@ -263,31 +260,35 @@ class WMF(RecModel):
         return it
 
     def _train_weighted(self, C_full, CT_full, util_d, iterations, verbose, eval_mat, cores, stopping_rounds,
-                        min_improvement, stats, rank_id, world, ub=None):
+                        min_improvement, stats, rank_id, world):
+        from .epoch import ResidentEpoch
         bias = self.bias is True
         algo = _ALGOS[self.algo]
         f = self.items.shape[1] if self.items is not None else self.dim
         distributed = world > 1
         if distributed:
+            ucounts = (C_full.indptr[1:] - C_full.indptr[:-1]).cpu().numpy()
             icounts = (CT_full.indptr[1:] - CT_full.indptr[:-1]).cpu().numpy()
-            if ub is None:
-                ucounts = (C_full.indptr[1:] - C_full.indptr[:-1]).cpu().numpy()
-                ub = sharding.balanced_row_partition(ucounts, world, f, align=engine.gram_block_rows(len(ucounts)))
+            ub = sharding.balanced_row_partition(ucounts, world, f, align=engine.gram_block_rows(len(ucounts)))
             ib = sharding.balanced_row_partition(icounts, world, f, align=engine.gram_block_rows(len(icounts)))
             C = C_full.row_slice(int(ub[rank_id]), int(ub[rank_id + 1]))
             CT = CT_full.row_slice(int(ib[rank_id]), int(ib[rank_id + 1]))
-            eval_d = self._eval_csr(eval_mat, ub, rank_id)
             u_lo, u_hi = int(ub[rank_id]), int(ub[rank_id + 1])
         else:
             C, CT, ub, ib = C_full, CT_full, None, None
-            eval_d = None  # uploaded lazily so a bad eval_mat fails where the reference fails (:163)
             u_lo, u_hi = 0, C_full.shape[0]
-        C.row_order, CT.row_order  # noqa: B018  (sort once, outside the epoch loop)
+        # the epoch's stages (half-step | exchange / Gram | half-step | exchange / Gram), launched eagerly:
+        # wmf_model.py:140-156. Row-sharded, the exchange runs over peer memory when it is available.
+        t_mark = time.perf_counter()
+        loop = ResidentEpoch(C, CT, self.items_device, self.gamma, bias=bias, algo=algo, ub=ub, ib=ib, graphs=False,
+                             count_launches=False)
+        stats.setdefault("host_marks_ms", []).append(("epoch object ready (+ms)", (time.perf_counter() - t_mark) * 1e3))
+        eval_d = None  # uploaded on a side stream so a bad eval_mat fails where the reference fails (:163)
         stats["setup_ms"] = 0.0
+        stats["exchange"] = loop.exchange_mode
         last_mse, count_improvement = -np.inf, 0
         it = None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        G_items = None
         side = getattr(self, "_side_stream", None)
         if side is None:
             side = self._side_stream = torch.cuda.Stream(device=self.device)
@@ -302,25 +303,16 @@ class WMF(RecModel):
                 raise ValueError(f"self.bias = {self.bias} is unknown. Only True / False are allowed.")
             start = time.time()
             ev[0].record()
-            # users from items (:143 / :151), then items from users (:144 / :152)
-            # Gram of the fixed side: on one GPU from the full matrix; row-sharded, every rank contributes the
-            # blocks of the shard it has just computed (same bits, see sharding.sharded_gram)
-            if G_items is None:
-                G_items = engine.gram(self.items_device, self.gamma, ones_col0=bias)
-            X = engine.half_step(C, self.items_device, G_items, bias=bias, algo=algo)
+            loop.run_stage(0)           # users from items (:143 / :151)
             if eval_d is None and eval_mat is not None:
                 # the evaluation matrix goes up on a side stream while the half-step runs (a missing one still
                 # fails below, where the reference fails, :163)
                 with torch.cuda.stream(side):
-                    eval_d = self._eval_csr(eval_mat)
+                    eval_d = self._eval_csr(eval_mat, ub, rank_id)
                     eval_ready = torch.cuda.Event()
                     eval_ready.record(side)
-            if distributed:
-                G = sharding.sharded_gram(X, ub, self.gamma, ones_col0=bias)
-                users = sharding.all_gather_rows(X, ub)
-            else:
-                G = engine.gram(X, self.gamma, ones_col0=bias)
-                users = X
+            loop.run_stage(1)           # Gram of the new users (+ exchange of the shards)
+            users = loop.users
             self._set_device_factors(users=users)
             ev[1].record()
             if it == iterations - 1:
@@ -333,26 +325,23 @@ class WMF(RecModel):
                     done.record(side)
                 users.record_stream(side)
                 self._users_prefetch = (users, host, done)
-            Xi = engine.half_step(CT, users, G, bias=bias, algo=algo)
-            if distributed:
-                G_items = sharding.sharded_gram(Xi, ib, self.gamma, ones_col0=bias)
-                items = sharding.all_gather_rows(Xi, ib)
-            else:
-                G_items = None
-                items = Xi
-            self._set_device_factors(items=items)
+            loop.run_stage(2)           # items from users (:144 / :152)
+            loop.run_stage(3)           # Gram of the new items for the next epoch (+ exchange of the shards)
+            self._set_device_factors(items=loop.items)
             ev[2].record()
             if eval_d is None:
-                eval_d = self._eval_csr(eval_mat)
+                eval_d = self._eval_csr(eval_mat, ub, rank_id)
             if eval_ready is not None:
                 cur = torch.cuda.current_stream(self.device)
                 cur.wait_event(eval_ready)
                 for t in (eval_d.indptr, eval_d.indices, eval_d.data):
                     t.record_stream(cur)
                 eval_ready = None
+            stats["host_marks_ms"].append((f"epoch {it} issued (+ms)", (time.perf_counter() - t_mark) * 1e3))
             mse_eval = self._mse_device(eval_d, self.users_device[u_lo:u_hi], distributed)
             ev[3].record()
             torch.cuda.synchronize(self.device)
+            stats["host_marks_ms"].append((f"epoch {it} done (+ms)", (time.perf_counter() - t_mark) * 1e3))
             stats["half_step_ms"].append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
             stats["eval_ms"].append(ev[2].elapsed_time(ev[3]))
             if bias and cores == 1:
@@ -371,6 +360,17 @@ class WMF(RecModel):
                 break
         if it is None:
             raise UnboundLocalError("cannot access local variable 'iter' where it is not associated with a value")
+        if loop.px is not None:
+            # the symmetric buffers are shared with the next training of the same shape: the model keeps its own copy
+            # (the read-back of the users already in flight reads the buffer, which nothing overwrites before the
+            # synchronisation at the end of train())
+            self._items_d = loop.items.clone()
+            if self._users_prefetch is None:
+                self._users_d = loop.users.clone()
+            else:
+                keep = loop.users.clone()
+                self._users_prefetch = (keep, self._users_prefetch[1], self._users_prefetch[2])
+                self._users_d = keep
         if verbose > 0:
             print("Training was completed.")
         if verbose > 1:

@@ -14,6 +14,9 @@ def T(label, fn, n=3):
 m = WMF(num_items=26744, num_users=138493, dim=128, gamma=0.1, weighted=True)
 T("train(iterations=1) total", lambda: m.train(tr, 1, eval_mat=te, count_mat=tr, cores=1, stopping_rounds=99))
 print(m.last_train_stats)
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable(); m.train(tr, 1, eval_mat=te, count_mat=tr, cores=1, stopping_rounds=99); u = m.users; pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
 Cd = T("DeviceCSR.from_scipy(train)", lambda: DeviceCSR.from_scipy(tr, dev))
 T("preprocess", lambda: engine.preprocess_(Cd.data.clone(), "log", 10, 1))
 CT = T("transpose", lambda: Cd.transpose())

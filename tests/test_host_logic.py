@@ -102,11 +102,8 @@ single = np.zeros((8, 8)); summed = np.zeros((8, 8))
 for b in range(nb):
     single = single + block(b, ref_u); summed = summed + part[b].numpy()
 assert np.array_equal(single, summed), "block partial exchange changed the Gram"
-# sharded upload: each rank contributes its own rows, every rank ends up with the full matrix
-from recmodel_b200.engine import DeviceCSR
-Cs = DeviceCSR.from_scipy_sharded(C, torch.device("cpu"), ub2)
-assert np.array_equal(Cs.indptr.numpy(), C.indptr) and np.array_equal(Cs.indices.numpy(), C.indices)
-assert np.array_equal(Cs.data.numpy(), C.data)
+# peer-memory exchange is a GPU feature: on CPU / gloo the buffers are unavailable and callers take the collective path
+assert sharding.PeerBuffers.create(90, 60, 8, torch.device("cpu")) is None
 s = torch.tensor([1.0 + rank, 2.0, 3.0], dtype=torch.float64)
 sharding.all_reduce_sum_(s)
 assert s.tolist() == [3.0, 4.0, 6.0]
