@@ -173,7 +173,7 @@ class WMF(RecModel):
             eval_mat = utility_mat
         rank_id, world = sharding.dist_info()
         dev = self.device
-        t_start = time.perf_counter()
+        t_start = self._t_train_start = time.perf_counter()
 
         util_d = None
         if preprocess_mat == True or verbose > 1 or self.weighted is not True:  # noqa: E712
@@ -280,6 +280,7 @@ class WMF(RecModel):
         # the epoch's stages (half-step | exchange / Gram | half-step | exchange / Gram), launched eagerly:
         # wmf_model.py:140-156. Row-sharded, the exchange runs over peer memory when it is available.
         t_mark = time.perf_counter()
+        stats.setdefault("host_marks_ms", []).append(("partition done", (t_mark - self._t_train_start) * 1e3))
         loop = ResidentEpoch(C, CT, self.items_device, self.gamma, bias=bias, algo=algo, ub=ub, ib=ib, graphs=False,
                              count_launches=False)
         stats.setdefault("host_marks_ms", []).append(("epoch object ready (+ms)", (time.perf_counter() - t_mark) * 1e3))
@@ -304,13 +305,6 @@ class WMF(RecModel):
             start = time.time()
             ev[0].record()
             loop.run_stage(0)           # users from items (:143 / :151)
-            if eval_d is None and eval_mat is not None:
-                # the evaluation matrix goes up on a side stream while the half-step runs (a missing one still
-                # fails below, where the reference fails, :163)
-                with torch.cuda.stream(side):
-                    eval_d = self._eval_csr(eval_mat, ub, rank_id)
-                    eval_ready = torch.cuda.Event()
-                    eval_ready.record(side)
             loop.run_stage(1)           # Gram of the new users (+ exchange of the shards)
             users = loop.users
             self._set_device_factors(users=users)
@@ -329,6 +323,14 @@ class WMF(RecModel):
             loop.run_stage(3)           # Gram of the new items for the next epoch (+ exchange of the shards)
             self._set_device_factors(items=loop.items)
             ev[2].record()
+            if eval_d is None and eval_mat is not None:
+                # the evaluation matrix goes up on a side stream while the epoch issued above runs (its host-side
+                # slicing and staging copy would otherwise sit between two stages and leave the GPU idle; a missing
+                # matrix still fails below, where the reference fails, :163)
+                with torch.cuda.stream(side):
+                    eval_d = self._eval_csr(eval_mat, ub, rank_id)
+                    eval_ready = torch.cuda.Event()
+                    eval_ready.record(side)
             if eval_d is None:
                 eval_d = self._eval_csr(eval_mat, ub, rank_id)
             if eval_ready is not None:
