@@ -192,6 +192,20 @@ int wmf_dense_right_multiply(const float* Y, int64_t n, int64_t ldy, const float
 int wmf_spmm(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows,
              const float* W, int64_t ldw, int f, float* X, int64_t ldx, void* stream);
 
+/* N4. EASE, the WMF path's dense sibling:                replaces Ease.train (RecModel/ease_model.py:81-114) and
+ * _predict_ease (RecModel/fast_utils/ease_utils.pyx:15-30).
+ * wmf_ease_train: W[n x n] (row-major, ld = n) = P / (-diag(P) + 1e-9) column-wise with a zero diagonal, where
+ * P = inv(X^T X + alpha I) and X is the `rows` x n interaction matrix in CSR (Gram by one warp per user row, blocked
+ * in-place Gauss-Jordan inverse in FP32: G is symmetric positive definite, no pivoting).
+ * wmf_ease_predict: out[k] = sum_j X[users[k*user_stride], j] * W[j, items[k]] with FP32 products summed in double in
+ * stored order (what the reference's Cython loop does); user_stride 0 broadcasts one user. */
+size_t wmf_ease_workspace_bytes(int64_t n);
+int wmf_ease_train(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows, int64_t n, float alpha,
+                   float* W, void* ws, size_t ws_bytes, void* stream);
+int wmf_ease_predict(const int64_t* indptr, const int32_t* indices, const float* data, const float* W, int64_t n,
+                     const int64_t* users, int64_t user_stride, const int64_t* items, int64_t count, double* out,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,3 +59,38 @@ def load_reference_wmf():
     wmf = importlib.import_module("RecModel.wmf_model")
     wmf.MKLThreads = _BlasThreads
     return wmf.WMF
+
+
+def load_reference_ease(build_dir="/tmp/wmf_ref_build"):
+    """Returns the reference's Ease class (RecModel/ease_model.py:45) with its Cython predictor
+    (RecModel/fast_utils/ease_utils.pyx) compiled from the sources where they lie, into ``build_dir``
+    (outside the repository; nothing of the reference is copied into the tree)."""
+    import shutil
+    import subprocess
+    load_reference_wmf()   # package stubs
+    os.makedirs(build_dir, exist_ok=True)
+    so = [f for f in os.listdir(build_dir) if f.startswith("ease_utils") and f.endswith(".so")]
+    if not so:
+        shutil.copy(os.path.join(REFERENCE_ROOT, "RecModel", "fast_utils", "ease_utils.pyx"), build_dir)
+        setup = ("from setuptools import setup, Extension\nfrom Cython.Build import cythonize\nimport numpy\n"
+                 "setup(ext_modules=cythonize([Extension('ease_utils', ['ease_utils.pyx'], include_dirs=[numpy.get_include()])], "
+                 "compiler_directives={'legacy_implicit_noexcept': True}))\n")
+        with open(os.path.join(build_dir, "setup.py"), "w") as fh:
+            fh.write(setup)
+        env = dict(os.environ, CC="/usr/bin/gcc")
+        subprocess.run([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=build_dir, env=env, check=True,
+                       capture_output=True)
+    if build_dir not in sys.path:
+        sys.path.insert(0, build_dir)
+    ease_utils = importlib.import_module("ease_utils")
+    fast = types.ModuleType("RecModel.fast_utils")
+    fast.__path__ = []
+    fast.ease_utils = ease_utils
+    sys.modules["RecModel.fast_utils"] = fast
+    sys.modules["RecModel.fast_utils.ease_utils"] = ease_utils
+    sm = sys.modules["sharedmem"]
+    if not hasattr(sm, "empty"):
+        import numpy as _np
+        sm.empty = lambda shape, dtype=_np.float32: _np.empty(shape, dtype=dtype)   # ease_model.py:110
+    ease = importlib.import_module("RecModel.ease_model")
+    return ease.Ease

@@ -320,3 +320,45 @@ def half_step_bytes(nnz, rows, cols, f, bias=False):
 
 def epoch_bytes(nnz, users, items, f, bias=False):
     return half_step_bytes(nnz, users, items, f, bias) + half_step_bytes(nnz, items, users, f, bias)
+
+
+# --------------------------------------------------------------------------------------------
+# EASE: restatement of /root/reference/RecModel/ease_model.py:81-114 and
+# /root/reference/RecModel/fast_utils/ease_utils.pyx:15-30
+# --------------------------------------------------------------------------------------------
+def ease_train(X, alpha, dtype=np.float32):
+    """W of the EASE model. dtype float32 follows the reference (ease_model.py:93-109); float64 is the yardstick."""
+    X_csr = X.copy().tocsr()
+    G = np.asarray(np.dot(X_csr.T, X_csr).todense()).astype(dtype)      # :93
+    np.fill_diagonal(G, G.diagonal() + dtype(alpha))                    # :97
+    res = np.linalg.inv(G)                                              # :102
+    res = res / (-res.diagonal() + 1e-9)                                # :106 (column-wise broadcast)
+    np.fill_diagonal(res, 0)                                            # :108
+    return res.astype(dtype if dtype == np.float64 else np.float32)     # :111
+
+
+def ease_predict(X, W, users, items):
+    """Per pair: sum over the user's stored entries of X[u, j] * W[j, item], FP32 products accumulated in
+    double in stored order (ease_utils.pyx:24-29: `output` is a float64 array, the product two C floats)."""
+    X_csr = X.tocsr()
+    users, items = np.atleast_1d(users), np.atleast_1d(items)
+    if len(users) == 0 or len(items) == 0:
+        return np.full(1, 0.0, dtype=np.float32)                        # :19-20
+    out = np.zeros(len(items))
+    W = np.asarray(W, dtype=np.float32)
+    for i in range(len(items)):
+        u = users[i] if len(users) > 1 else users[0]
+        lo, hi = X_csr.indptr[u], X_csr.indptr[u + 1]
+        prod = (X_csr.data[lo:hi].astype(np.float32) * W[X_csr.indices[lo:hi], items[i]]).astype(np.float32)
+        acc = 0.0
+        for p in prod:
+            acc += float(p)
+        out[i] = acc
+    return out
+
+
+def ease_rank(X, W, items, user, topn):
+    """ease_model.py:51-53."""
+    items = np.asarray(items)
+    pred = ease_predict(X, W, np.full(items.shape[0], user, dtype=np.int32), items.astype(np.int32))
+    return items[np.argpartition(pred, list(range(-topn, 0, 1)))[-topn:]][::-1]

@@ -594,7 +594,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         const int q = warp & 3;        // TMEM lane quarter this warp may access
         const int t = q * 32 + lane;   // matrix row owned by this thread = TMEM lane
         const int bar_id = 1 + g;
-        const int ISSUE_T = WMF_TC_BALANCED ? 32 * g : 0;  // thread of the group that issues its rank-8 update MMAs
+        const int ISSUE_T = 32 * g;  // thread of the group that issues its rank-8 update MMAs
         const uint32_t gs = smem_base + OFF_GROUPS + g * GROUP_BYTES;
         const uint32_t tileH = gs + G_OFF_TILEH, tileL = gs + G_OFF_TILEL;
         const uint32_t Nst = gs + G_OFF_NINV, zst = gs + G_OFF_ZB, Dblk = gs + G_OFF_DBLK, bfin = gs + G_OFF_BFIN;
@@ -697,7 +697,6 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 for (int i = 0; i < NB; ++i) a[i] = fmaf(a[i], inv_s2, rel == i ? 1.0f : 0.0f);  // I + sum d y~ y~^T
                 if (prof) { t3 = clock64(); ph_ld += t3 - t4; }
                 const uint32_t nd = Nst + (c0 >> 3) * 256, zd = zst + (c0 >> 3) * 32;
-#if WMF_TC_BALANCED
                 // The 8 threads that hold the pivot rows publish them; the serial 8x8 factor is run by warp g of
                 // group g, whatever warp the pivot rows live in: the four groups' serial chains then sit on four
                 // different warp schedulers (warp id mod 4) instead of piling up on the scheduler of the quarter all
@@ -709,16 +708,6 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 }
                 named_bar(bar_id, GROUP);
                 if (q == g) {
-#else
-                if (q == (c0 >> 5)) {
-                    // ---- owner warp: Cholesky of the 8x8 pivot block, its inverse N = L^-1, zb = N b_blk ----
-                    if (rel >= 0 && rel < NB) {
-                        sts4(Dblk + rel * 32, a[0], a[1], a[2], a[3]);
-                        sts4(Dblk + rel * 32 + 16, a[4], a[5], a[6], a[7]);
-                        sts1(Dblk + 256 + rel * 4, bt);
-                    }
-                    __syncwarp();
-#endif
                     float d[36], bb[NB];
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {

@@ -4,12 +4,6 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 
-// 1: the serial pivot-block factor and the MMA issue of solver group g run on warp g of the group (one group per
-// warp scheduler); 0: on the warp that holds the pivot rows / on warp 0 (the round-1 arrangement, kept for A/B runs)
-#ifndef WMF_TC_BALANCED
-#define WMF_TC_BALANCED 1
-#endif
-
 namespace wmf {
 namespace tc {
 

@@ -511,3 +511,32 @@ def unweighted_half_step(csr, Y, lam):
     _lib.check(lib.wmf_spmm(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), csr.shape[0], _ptr(W), W.stride(0), f,
                             _ptr(X), X.stride(0), _stream()), "wmf_spmm")
     return X
+
+
+@_device_of(0)
+def ease_train(csr, alpha):
+    """W of the EASE model for the interaction matrix ``csr`` (ease_model.py:81-114): dense [items x items] float32."""
+    lib = _lib.load()
+    n = csr.shape[1]
+    W = torch.empty((n, n), dtype=torch.float32, device=csr.device)
+    ws = workspace(lib.wmf_ease_workspace_bytes(n), csr.device)
+    _lib.check(lib.wmf_ease_train(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), csr.shape[0], n, float(alpha), _ptr(W),
+                                  _ptr(ws), ws.numel(), _stream()), "wmf_ease_train")
+    return W
+
+
+@_device_of(1)
+def ease_predict(csr, W, users, items):
+    """float64 scores sum_j X[user, j] W[j, item] of (users[k], items[k]); one user broadcasts (ease_utils.pyx:15-30)."""
+    lib = _lib.load()
+    _f32(W)
+    n = items.numel()
+    stride = 1
+    if users.numel() == 1 and n != 1:
+        stride = 0
+    elif users.numel() != n:
+        raise ValueError("users and items need to have the same length or only one user needs to be provided.")
+    out = torch.empty(n, dtype=torch.float64, device=W.device)
+    _lib.check(lib.wmf_ease_predict(_ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), _ptr(W), W.shape[0], _ptr(users), stride,
+                                    _ptr(items), n, _ptr(out), _stream()), "wmf_ease_predict")
+    return out

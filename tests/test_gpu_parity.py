@@ -677,3 +677,61 @@ def test_half_step_dual_rows_every_length(cuda_device, f, bias):
         np.testing.assert_array_equal(X, X2)
         Xa, _ = run_half_step(Y, C[:40], bias, _lib.ALGO_TCGEN05, cuda_device)   # row sharding never changes a row's bits
         np.testing.assert_array_equal(Xa, X[:40])
+
+
+# ------------------------------------------------------------------------------- larger golden fixture, EASE (N4)
+@pytest.mark.parametrize("algo_name,algo", ALGOS)
+def test_half_step_vs_reference_golden_2000x1500(cuda_device, algo_name, algo):
+    """The executed reference at 2000 x 1500, f = 128 (tests/golden/make_golden.py::case_half_steps): both tensor-core
+    kernels (dual for the short rows, primal for the rest) against reference output, not only against the oracle."""
+    g = load_golden("weighted_nobias_f128_2000x1500")
+    C = csr_from(g, "train")
+    C.data = orc.preprocess_counts(C.data)
+    CT = C.T.tocsr()
+    X, _ = run_half_step(g["items0"], C, False, algo, cuda_device)
+    rows = np.arange(0, 2000, 5)
+    check_half_step("golden/2000x1500_f128/users_half1", algo_name, X[rows], g["users_half1"][rows],
+                    orc.half_step(g["items0"], C[rows], 0.1, np.float64))
+    Xi, _ = run_half_step(g["users_half1"], CT, False, algo, cuda_device)
+    rows = np.arange(0, 1500, 5)
+    check_half_step("golden/2000x1500_f128/items_half1", algo_name, Xi[rows], g["items_half1"][rows],
+                    orc.half_step(g["users_half1"], CT[rows], 0.1, np.float64), steady=True)
+
+
+def test_ease_vs_reference_golden(cuda_device):
+    """N4: Ease.train / predict / rank / eval_topn on the device against the executed reference (its Cython predictor
+    compiled from the reference sources when the fixture was made)."""
+    from recmodel_b200.ease_model import Ease
+    g = load_golden("ease_f300")
+    X, te = csr_from(g, "train"), csr_from(g, "test")
+    m = Ease(num_items=X.shape[1], num_users=X.shape[0])
+    m.train(X.copy(), alpha=float(g["alpha"]), verbose=0, cores=1)
+    W = m.W
+    scale = np.abs(g["W"]).max()
+    W64 = orc.ease_train(X, float(g["alpha"]), np.float64)
+    err_ref, err64, noise = np.abs(W - g["W"]).max() / scale, np.abs(W - W64).max() / scale, np.abs(g["W"] - W64).max() / scale
+    print(f"EASE W: vs reference {err_ref:.2e}, vs fp64 {err64:.2e}; reference vs fp64 {noise:.2e}")
+    assert W.dtype == np.float32 and np.all(np.diag(W) == 0)
+    assert err64 < 1e-4 and err_ref < 1e-4
+    # prediction arithmetic is bit-exact given the same W
+    m.W = g["W"]
+    np.testing.assert_array_equal(m.predict(g["pred_users"], g["pred_items"]), g["pred"])
+    for k, u in enumerate(g["rank_users"]):
+        np.testing.assert_array_equal(m.rank(np.arange(X.shape[1]), int(u), 10), g["rank_top10"][k])
+    rec = m.eval_topn(te.copy(), topn=g["topn"], rand_sampled=100, cores=1, random_state=7)
+    np.testing.assert_allclose([rec[f"Recall@{k}"] for k in g["topn"]], g["recall"], atol=1e-12)
+    assert m.predict(np.array([], dtype=np.int32), np.array([], dtype=np.int32)).shape == (1,)
+
+
+def test_ease_larger_matrix_against_fp64(cuda_device):
+    """A catalogue that spans many panels of the blocked inverse (1 100 items, not a multiple of the 64-wide panel)."""
+    from recmodel_b200.ease_model import Ease
+    X = make_counts(3000, 1100, 90_000, seed=3, planted_rank=6)
+    m = Ease(num_items=1100, num_users=3000)
+    m.train(X, alpha=100.0, verbose=0, cores=1)
+    W64 = orc.ease_train(X, 100.0, np.float64)
+    W32 = orc.ease_train(X, 100.0)
+    scale = np.abs(W64).max()
+    err, noise = np.abs(m.W - W64).max() / scale, np.abs(W32 - W64).max() / scale
+    print(f"EASE 1100 items: gpu vs fp64 {err:.2e}; numpy fp32 vs fp64 {noise:.2e}")
+    assert err < max(1e-4, 3 * noise)

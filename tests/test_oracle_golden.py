@@ -178,3 +178,32 @@ def test_live_reference_if_mounted():
     ref = m.recompute_factors(m.items, C, 0.1)
     np.testing.assert_array_equal(ref, g["users_half1"])
     assert row_rel_err(orc.half_step(g["items0"], C, 0.1), ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------- larger f = 128 fixture, EASE (N4)
+def test_large_f128_half_steps_fp32_and_fp64():
+    """2000 x 1500 fixture of the executed reference (tests/golden/make_golden.py::case_half_steps): the oracle's
+    fp32 arithmetic reproduces it to BLAS rounding, the fp64 restatement within the first-half-step noise."""
+    g = load_golden("weighted_nobias_f128_2000x1500")
+    C = csr_from(g, "train")
+    C.data = orc.preprocess_counts(C.data)
+    rows = slice(0, 300)
+    u32 = orc.half_step(g["items0"], C[rows], 0.1)
+    assert row_rel_err(u32, g["users_half1"][rows]) < 2e-4   # same formula, thread-count dependent BLAS rounding
+    u64 = orc.half_step(g["items0"], C[rows], 0.1, np.float64)
+    assert row_rel_err(g["users_half1"][rows], u64) < 5e-4
+
+
+def test_ease_oracle_matches_executed_reference():
+    g = load_golden("ease_f300")
+    X = csr_from(g, "train")
+    W = orc.ease_train(X, float(g["alpha"]))
+    assert W.dtype == np.float32 and np.all(np.diag(W) == 0)
+    scale = np.abs(g["W"]).max()
+    assert np.max(np.abs(W - g["W"])) < 1e-5 * scale            # same LAPACK call, same dtype
+    W64 = orc.ease_train(X, float(g["alpha"]), np.float64)
+    assert np.max(np.abs(g["W"] - W64)) < 1e-4 * scale          # the reference's own fp32 noise
+    pred = orc.ease_predict(X, g["W"], g["pred_users"], g["pred_items"])
+    np.testing.assert_array_equal(pred, g["pred"])              # restated accumulation order is bit-exact
+    for k, u in enumerate(g["rank_users"][:6]):
+        np.testing.assert_array_equal(orc.ease_rank(X, g["W"], np.arange(X.shape[1]), int(u), 10), g["rank_top10"][k])
