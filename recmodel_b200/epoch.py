@@ -62,6 +62,8 @@ class ResidentEpoch:
         need = max(engine.half_step_workspace_bytes(C, f, algo), engine.half_step_workspace_bytes(CT, f, algo),
                    int(lib.wmf_gram_workspace_bytes(max(n_users, n_items), f)))
         self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._side = torch.cuda.Stream(device=dev) if self.px is not None else None
+        self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
         self.stages = [self._user_half_step, self._user_exchange, self._item_half_step, self._item_exchange]
         self.graphs = None
         self.launches_per_epoch = 0
@@ -84,9 +86,16 @@ class ResidentEpoch:
             lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
             B = engine.gram_block_rows(n_total)
             gp = self.px.views["gp_" + name]
-            self.px.push(name, lo, hi)                                        # new factor rows -> every peer
+            # the rows travel over NVLink on a side stream while the Gram blocks of the shard are computed
+            cur = torch.cuda.current_stream(X.device)
+            self._fork.record(cur)
+            self._side.wait_event(self._fork)
+            with torch.cuda.stream(self._side):
+                self.px.push(name, lo, hi)                                    # new factor rows -> every peer
+                self._join.record(self._side)
             engine.gram_partials(X, lo, n_total, ones_col0=self.bias, out=gp)  # Gram blocks of the shard
             self.px.push("gp_" + name, lo // B, -(-hi // B))                   # ... -> every peer
+            cur.wait_event(self._join)
             self.px.barrier()
             engine.gram_from_partials(gp, n_total, self.gamma, out=G_out)      # all blocks in block order
         elif self.world > 1:

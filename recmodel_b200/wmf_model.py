@@ -65,10 +65,14 @@ class WMF(RecModel):
     def _to_device(self, arr):
         return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
 
+    # ``users`` / ``items`` are plain ndarrays in the reference (wmf_model.py:15-18). Here the device tensor is the
+    # source of truth and the getters hand out a cached host copy, marked READ-ONLY so that an in-place edit cannot be
+    # silently ignored: assign a whole array (``m.items = new``) to change the factors.
     @property
     def items(self):
         if self._items_h is None and self._items_d is not None:
             self._items_h = engine.d2h(self._items_d)
+            self._items_h.setflags(write=False)
         return self._items_h
 
     @items.setter
@@ -85,6 +89,7 @@ class WMF(RecModel):
                 self._users_h = pre[1].numpy()
             else:
                 self._users_h = engine.d2h(self._users_d)
+            self._users_h.setflags(write=False)
             self._users_prefetch = None
         return self._users_h
 
@@ -482,7 +487,8 @@ class WMF(RecModel):
         """Bias formula (wmf_model.py:311-351). Like the reference (:331) the caller's Y has its
         column 0 set to 1 afterwards; the kernel itself reads the bias from the unmodified copy."""
         X = self._half_step_host(Y, C, lambda_reg, True)
-        Y[:, 0] = 1
+        if isinstance(Y, np.ndarray) and Y.flags.writeable:
+            Y[:, 0] = 1
         return X
 
     def recompute_factors_bias_par(self, Y, C, lambda_reg, cores=3):
