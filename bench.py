@@ -504,6 +504,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "nnz-updates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()) * 1e3,
                     "ms_steps_rank0": [round(t * 1e3, 2) for t in times],
+                    "host_marks_ms_last_step": [(k, round(v, 2)) for k, v in model.last_train_stats.get("host_marks_ms", [])],
+                    "device_ms_last_step": {"half_steps": model.last_train_stats.get("half_step_ms"),
+                                            "eval": model.last_train_stats.get("eval_ms")},
                     "what": "WMF.train(host CSR, iterations=1) incl. upload, preprocess, transpose, epoch, eval_prec, "
                             "factor read-back; 80/20 split so nnz = train nnz"},
             "gpu_launches": int(launches_per_epoch * args.steps),

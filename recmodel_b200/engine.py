@@ -64,26 +64,20 @@ def default_device():
 _pinned = {}
 
 
-_copy_pool = None
-
-
 def _host_copy(dst, src):
-    """dst[:] = src for large contiguous NumPy arrays, split over a few Python threads (NumPy's memcpy releases the
-    GIL). torch's own CPU copy follows OMP_NUM_THREADS, which torchrun sets to 1: the staging copy of a 128 MB matrix
-    then took 18 ms per rank instead of 4."""
-    global _copy_pool
-    n = src.shape[0]
-    workers = max(1, min(8, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-    if n < (1 << 20) or workers == 1:
-        np.copyto(dst, src)
+    """dst.copy_(src) for large CPU tensors with enough threads. torch's CPU copy follows its intra-op thread count,
+    which torchrun pins to 1 through OMP_NUM_THREADS: the staging copy of a 128 MB matrix then took 18 ms per rank
+    instead of 2-4 (scripts/dev/host_copy_bench.py). The count is raised for the copy and restored afterwards."""
+    have = torch.get_num_threads()
+    want = max(1, min(8, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if have >= want or src.numel() < (1 << 20):
+        dst.copy_(src)
         return
-    if _copy_pool is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _copy_pool = ThreadPoolExecutor(max_workers=8)
-    step = -(-n // workers)
-    futs = [_copy_pool.submit(np.copyto, dst[i:i + step], src[i:i + step]) for i in range(0, n, step)]
-    for fu in futs:
-        fu.result()
+    torch.set_num_threads(want)
+    try:
+        dst.copy_(src)
+    finally:
+        torch.set_num_threads(have)
 
 
 def _h2d(arr, dtype, device):
@@ -102,7 +96,7 @@ def _h2d(arr, dtype, device):
     buf, busy = ent
     if busy is not None:
         busy.synchronize()  # the previous transfer out of this staging buffer has finished
-    _host_copy(buf[:n].numpy(), a.reshape(-1))
+    _host_copy(buf[:n], t.reshape(-1))
     out = buf[:n].to(device, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(device))

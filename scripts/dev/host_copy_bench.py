@@ -13,7 +13,7 @@ def T(label, fn, reps=5):
     print(f"rank {os.environ.get('RANK', 0)} threads(torch)={torch.get_num_threads()} OMP={os.environ.get('OMP_NUM_THREADS')} cpus={os.cpu_count()} {label:40s} min {min(ts)*1e3:6.2f} ms  median {sorted(ts)[len(ts)//2]*1e3:6.2f} ms", flush=True)
 T("torch copy_ (current threads)", lambda: buf.copy_(t))
 T("np.copyto single", lambda: np.copyto(buf.numpy(), a))
-T("engine._host_copy (thread pool)", lambda: engine._host_copy(buf.numpy(), a))
+T("engine._host_copy", lambda: engine._host_copy(buf, t))
 old = torch.get_num_threads()
 for k in (4, 8, 16):
     torch.set_num_threads(k)
