@@ -461,6 +461,14 @@ def run_ours(args):
             sync_all()
             t, d2h = e2e_step()
             times.append(t)
+        if os.environ.get("WMF_BENCH_PROFILE"):   # development: where does the host spend an e2e step?
+            import cProfile
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            e2e_step()
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(30)
         h2d = (tr_host.nnz * 8 + (users + 1) * 8) + (te_host.nnz * 8 + (users + 1) * 8)
         e2e_nnz = tr_host.nnz
     else:

@@ -65,12 +65,13 @@ _pinned = {}
 
 
 def _host_copy(dst, src):
-    """dst.copy_(src) for large CPU tensors with enough threads. torch's CPU copy follows its intra-op thread count,
-    which torchrun pins to 1 through OMP_NUM_THREADS: the staging copy of a 128 MB matrix then took 18 ms per rank
-    instead of 2-4 (scripts/dev/host_copy_bench.py). The count is raised for the copy and restored afterwards."""
+    """dst.copy_(src) for large CPU tensors with a fixed, moderate thread count. torch's CPU copy follows its intra-op
+    thread count: torchrun pins it to 1 through OMP_NUM_THREADS (18 ms per rank for a 128 MB matrix instead of 2-4),
+    and with one thread per logical CPU of a shared host a single descheduled thread stalls the whole copy (1.0 ms
+    median, 11 ms worst for 64 MB with 16 threads; 1.6 / 1.9 ms with 8: scripts/dev/host_copy_noise.py)."""
     have = torch.get_num_threads()
     want = max(1, min(8, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-    if have >= want or src.numel() < (1 << 20):
+    if have == want or src.numel() < (1 << 20):
         dst.copy_(src)
         return
     torch.set_num_threads(want)
