@@ -23,7 +23,7 @@ from . import _lib, engine, sharding
 
 class ResidentEpoch:
     def __init__(self, C, CT, items0, gamma, bias=False, algo=_lib.ALGO_AUTO, ub=None, ib=None, graphs=True, peer=True,
-                 count_launches=True):
+                 count_launches=True, shared_ws=False):
         """C / CT: this rank's row slices (DeviceCSR) of the count matrix and of its transpose; ub / ib: shard
         boundaries (None on one GPU); items0: full initial item factors on the device; peer: exchange over peer
         memory when it is available (else NCCL)."""
@@ -61,7 +61,12 @@ class ResidentEpoch:
         lib = _lib.load()
         need = max(engine.half_step_workspace_bytes(C, f, algo), engine.half_step_workspace_bytes(CT, f, algo),
                    int(lib.wmf_gram_workspace_bytes(max(n_users, n_items), f)))
-        self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        # (an eager, un-captured epoch - WMF.train - may borrow the cache instead: a fresh ~0.5 GB allocation per
+        # train() call intermittently misses the caching allocator and costs 10 ms of cudaMalloc)
+        if shared_ws and not graphs:
+            self.ws = engine.workspace(need, dev)
+        else:
+            self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
         self._side = torch.cuda.Stream(device=dev) if self.px is not None else None
         self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
         self.stages = [self._user_half_step, self._user_exchange, self._item_half_step, self._item_exchange]

@@ -287,7 +287,7 @@ class WMF(RecModel):
         t_mark = time.perf_counter()
         stats.setdefault("host_marks_ms", []).append(("partition done", (t_mark - self._t_train_start) * 1e3))
         loop = ResidentEpoch(C, CT, self.items_device, self.gamma, bias=bias, algo=algo, ub=ub, ib=ib, graphs=False,
-                             count_launches=False)
+                             count_launches=False, shared_ws=True)
         stats.setdefault("host_marks_ms", []).append(("epoch object ready (+ms)", (time.perf_counter() - t_mark) * 1e3))
         eval_d = None  # uploaded on a side stream so a bad eval_mat fails where the reference fails (:163)
         stats["setup_ms"] = 0.0
