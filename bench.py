@@ -332,7 +332,8 @@ def run_ours(args):
         run_rank(args, device, world, rank)
         finish(world, device)
         return
-    algo = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tcgen05": _lib.ALGO_TCGEN05}[args.algo]
+    algo = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tcgen05": _lib.ALGO_TCGEN05,
+            "tcgen05_direct": _lib.ALGO_TCGEN05_DIRECT}[args.algo]
     users, items, _, dim, where, _ = WORKLOADS[args.workload]
     f = dim
 
@@ -554,7 +555,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="ml20m")
-    ap.add_argument("--algo", choices=["auto", "simt", "tcgen05"], default="auto")
+    ap.add_argument("--algo", choices=["auto", "simt", "tcgen05", "tcgen05_direct"], default="auto")
     ap.add_argument("--cpu-frac", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel tuning runs: skip the end-to-end leg (the line's e2e is NaN)")

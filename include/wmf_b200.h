@@ -39,7 +39,8 @@ extern "C" {
 /* Half-step algorithm selector */
 #define WMF_ALGO_AUTO 0
 #define WMF_ALGO_SIMT 1    /* FP32 CUDA-core Gram + Cholesky/LU; any f <= WMF_MAX_F; accuracy cross-check */
-#define WMF_ALGO_TCGEN05 2 /* whitened factors, FP16-split tcgen05 Gram + Gauss-Jordan in TMEM; f <= 256, biases included */
+#define WMF_ALGO_TCGEN05 2 /* whitened factors, FP16-split tcgen05 Gram, conjugate gradients on the matrix in TMEM; f <= 256, biases included */
+#define WMF_ALGO_TCGEN05_DIRECT 3 /* same pipeline, every system factorised (block Gauss-Jordan in TMEM): the fallback of 2, selectable as a cross-check */
 
 /* Count preprocessing modes */
 #define WMF_PREPROCESS_LOG 0    /* d = alpha*log(1+beta*x)   wmf_model.py:120 */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # WMF_B200_LIB (development only): another build of the same sources, e.g. the -DWMF_WATCHDOG variant
 LIB_PATH = os.environ.get("WMF_B200_LIB") or os.path.join(_HERE, "csrc", "libwmf_b200.so")
 
-ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_DIRECT = 0, 1, 2, 3
 PREPROCESS_LOG, PREPROCESS_LINEAR = 0, 1
 ERR_NAMES = {1: "INVALID", 2: "WORKSPACE", 3: "CUDA", 4: "NO_DEVICE", 5: "UNSUPPORTED"}
 TOPK_MAX = 1024

@@ -35,6 +35,8 @@ struct HalfStepParams {
     int* fix_list;      // rows the CUDA-core LU kernel solves afterwards (negative weights, failed pivot)
     int* fix_count;
     int nd_max;         // rows with at most this many entries take the dual (n x n) kernel
+    int cg_maxit;       // matrix-vector products the conjugate-gradient solver may spend on a row before the in-TMEM
+                        // factorisation takes it; 0: factorisation only (WMF_ALGO_TCGEN05_DIRECT)
 };
 
 size_t simt_half_step_workspace_bytes(int f);
@@ -45,6 +47,7 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
 // dual (n x n) kernel for the rows of the dual table (half_step_dual.cu)
 int tc_dual_launch(const HalfStepParams& p, const int4* dtab, const uint32_t* hdr_u, int grid, cudaStream_t st);
 int tc_dual_max_entries();
+int tc_cg_max_products();   // default budget of the conjugate-gradient solver (WMF_TC_CG=<n> overrides, 0 = off)
 // primal kernel for 128 < f <= 256 (half_step_tc256.cu); same tables and scratch conventions as the 128-wide one
 size_t tc256_part_floats();
 int tc256_launch(const HalfStepParams& p, const int4* tab, const int4* segtab, float* parts, int* counters,

@@ -18,7 +18,7 @@ int wmf_als_row_split_entries(void) { return wmf_tc_split_length(); }
 
 int wmf_als_half_step_supports(int algo, int f, int bias) {
     if (f <= 0 || f > WMF_MAX_F || (bias && f < 2)) return 0;
-    if (algo == WMF_ALGO_TCGEN05) return tc_half_step_supported(f, bias) ? 1 : 0;
+    if (algo == WMF_ALGO_TCGEN05 || algo == WMF_ALGO_TCGEN05_DIRECT) return tc_half_step_supported(f, bias) ? 1 : 0;
     return (algo == WMF_ALGO_SIMT || algo == WMF_ALGO_AUTO) ? 1 : 0;
 }
 
@@ -59,7 +59,7 @@ int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float
     WMF_REQUIRE(cols >= 0 && cols < (1ll << 31), "wmf_als_half_step: cols=%lld out of range", (long long)cols);
     if (rows == 0) return WMF_OK;
     WMF_REQUIRE(indptr && Y && G && X && ldy >= f && ldx >= f, "wmf_als_half_step: null pointer or short leading dimension");
-    WMF_REQUIRE(algo == WMF_ALGO_AUTO || algo == WMF_ALGO_SIMT || algo == WMF_ALGO_TCGEN05,
+    WMF_REQUIRE(algo == WMF_ALGO_AUTO || algo == WMF_ALGO_SIMT || algo == WMF_ALGO_TCGEN05 || algo == WMF_ALGO_TCGEN05_DIRECT,
                 "wmf_als_half_step: unknown algo %d", algo);
     const int chosen = resolve_algo(algo, f, bias);
     HalfStepParams p{};
@@ -67,7 +67,8 @@ int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float
     p.indptr = indptr; p.indices = indices; p.data = data; p.rows = rows; p.row_order = row_order;
     p.sched_len = row_order ? order_len : rows;
     p.Y = Y; p.ldy = ldy; p.f = f; p.G = G; p.bias = bias; p.X = X; p.ldx = ldx; p.cols = cols;
-    if (chosen == WMF_ALGO_TCGEN05) {
+    if (chosen == WMF_ALGO_TCGEN05 || chosen == WMF_ALGO_TCGEN05_DIRECT) {
+        p.cg_maxit = chosen == WMF_ALGO_TCGEN05_DIRECT ? 0 : tc_cg_max_products();
         if (!tc_half_step_supported(f, bias)) {
             set_error("wmf_als_half_step: the tcgen05 path takes f <= 256 (f=%d, bias=%d)", f, bias);
             return WMF_ERR_UNSUPPORTED;

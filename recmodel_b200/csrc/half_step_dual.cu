@@ -23,6 +23,7 @@
 #include "tc_common.cuh"
 #include "half_step.cuh"
 #include "factor8.cuh"
+#include "cg_solve.cuh"
 
 namespace wmf {
 
@@ -44,6 +45,7 @@ constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WAR
 constexpr int THREADS = (MMA_WARP + 1) * 32;  // 800
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int ACC_COLS = 128;
+constexpr int CG_BAR0 = 1 + NGROUP;   // named barriers 1 .. NGROUP: a whole solver group; CG_BAR0 + g: its warps that hold rows
 
 constexpr int PANEL_TILE_BYTES = 128 * NB * 4;
 constexpr int G_OFF_TILEH = 0;
@@ -271,6 +273,27 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
             // a warp whose 32 lanes lie beyond the padded system (n <= 32: three of the four) owns no matrix row: it
             // only keeps the group's barriers (and, if it is warp g, the pivot factor) and skips the per-row work
             const bool active = qw * 32 < n16;
+            // ---- default solver: conjugate gradients against the matrix in tensor memory (cg_solve.cuh); the block
+            // Gauss-Jordan below takes the rows that have not converged within p.cg_maxit products
+            bool solved = false;
+            float coef = 0.0f;
+            if (p.cg_maxit > 0) {
+                float xc = 0.0f;
+                int products = -1;
+                if (active) products = cg_solve(t_row, t, n16, bt, inv_s2, bfin, Dblk, qw, (n16 + 31) >> 5, CG_BAR0 + g, ((n16 + 31) >> 5) * 32, p.cg_maxit, xc);
+                const uint32_t flag = Dblk + 128u + (rn & 4u);   // alternates between this group's consecutive rows
+                if (t == 0) sts1(flag, products >= 0 ? 1.0f : 0.0f);
+                tc_fence_before();
+                named_bar(bar_id, GROUP);
+                solved = lds1(flag) != 0.0f;
+                if (solved) {
+                    mbar_arrive(bar_acc_empty(g));   // the Gram of this group's next row may start
+                    coef = t < n ? xc * sq : 0.0f;
+                } else {
+                    tc_fence_after();
+                }
+            }
+            if (!solved) {
 #pragma unroll 1
             for (int c0 = 0; c0 < n8; c0 += NB) {
                 if (c0 > 0) {  // the previous step's rank-8 update has landed in TMEM
@@ -417,10 +440,11 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                         xt = fmaf(nsel, y, xt);
                     }
                 }
-                const float coef = t < n ? xt * inv_s2 * sq : 0.0f;   // N was stored as S N
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pairs + (uint32_t)t * 8u), "r"(__float_as_uint(coef)),
-                             "r"((uint32_t)my_idx) : "memory");
+                coef = t < n ? xt * inv_s2 * sq : 0.0f;   // N was stored as S N
             }
+            }  // factorisation
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pairs + (uint32_t)t * 8u), "r"(__float_as_uint(coef)),
+                         "r"((uint32_t)my_idx) : "memory");
             named_bar(bar_id, GROUP);
             // ---- x'[m] = sum_j coef_j y~_j[m]: thread t sums feature t (and t + 128), entries in ascending order ----
             {

@@ -44,6 +44,7 @@
 #include "half_step.cuh"
 #include "whiten.cuh"
 #include "factor8.cuh"
+#include "cg_solve.cuh"
 
 namespace wmf {
 
@@ -74,6 +75,7 @@ constexpr int TEAM = 128;
 constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WARP0 + NTEAM * 4;  // high warp ids issue first
 constexpr int THREADS = (MMA_WARP + 1) * 32;               // 800
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int CG_BAR0 = 1 + NGROUP;  // named barriers 1 .. NGROUP: a whole solver group; CG_BAR0 + g: its warps that hold rows
 static_assert(NGROUP * F <= 512, "TMEM columns");
 
 // per-group shared memory
@@ -115,6 +117,13 @@ static int split_len() {
     static const int v = [] { int x = env_int_once("WMF_TC_SPLIT", SPLIT_LEN_DEFAULT); if (x < 64) x = SPLIT_LEN_DEFAULT; return (x + 31) / 32 * 32; }();
     return v;
 }
+}  // namespace tc
+// 64 products cover condition numbers up to ~100 (weights in the hundreds); beyond that the factorisation is cheaper
+int tc_cg_max_products() {
+    static const int v = [] { int x = tc::env_int_once("WMF_TC_CG", 64); return x < 0 ? 0 : (x > 1000 ? 1000 : x); }();
+    return v;
+}
+namespace tc {
 static bool dual_enabled() { static const bool v = env_int_once("WMF_TC_DUAL", 1) != 0; return v; }
 static bool profile_enabled() {
 #ifdef WMF_TC_PROFILE_BUILD
@@ -408,15 +417,19 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
             if (cu_k < nslots) {
                 const int off = cu_c * SUB + lane;
                 if (off < cu_n) {
+                    // Loads only: nothing here may depend on their results. They are first touched one pipeline step
+                    // later (issue()); a dependent instruction placed here (the bias look-up used to be) parks the warp
+                    // on the full global-load latency in every step, whether or not its predicate is set (ncu: half
+                    // of the gather warps' time).
                     rw.d = __ldg(p.data + cu_lo + off);
                     rw.idx = __ldg(p.indices + cu_lo + off);
-                    if (p.bias) rw.d = __fsub_rn(rw.d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
                 }
             }
             return rw;
         };
-        auto issue = [&](const Raw& rw, int buf) {
+        auto issue = [&](Raw rw, int buf) {
             const int wb = wbuf0 + buf;
+            if (p.bias && rw.idx >= 0) rw.d = __fsub_rn(rw.d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
             __syncwarp();  // the buffer's previous contents have been read by every lane
             {
                 float sq = 0.f, dp1 = 0.f;
@@ -605,10 +618,11 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         // a warp whose 32 lanes lie beyond the live width (f <= 64: two of the four) owns no matrix row: it only keeps
         // the group's barriers (and, if it is warp g, the pivot factor) and skips the per-row work
         const bool active = q * 32 < f16;
+        const int nact = (f16 + 31) >> 5;   // warps of the group that hold matrix rows
         uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
-        long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0, my_rows = 0;
+        long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0, my_rows = 0, cg_rows = 0, cg_products = 0;
         RowEnt nxt = ent_at(0);
         for (int k = 0; k < nslots; ++k) {
             const RowEnt e = nxt;
@@ -676,6 +690,26 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 for (int k2 = 0; k2 < sg.y; ++k2) bt += __ldcg(first + (size_t)k2 * PART_FLOATS + F * F + t);
                 tc_fence_before();
                 named_bar(bar_id, GROUP);
+                tc_fence_after();
+            }
+            // ---- default solver: conjugate gradients against the matrix in tensor memory (cg_solve.cuh). The block
+            // Gauss-Jordan below takes the rows that have not converged within p.cg_maxit products (and every row when
+            // p.cg_maxit == 0: WMF_ALGO_TCGEN05_DIRECT).
+            if (p.cg_maxit > 0) {
+                float xc = 0.0f;
+                int products = -1;
+                if (active) products = cg_solve(t_row, t, f16, bt, inv_s2, bfin, Dblk, q, nact, CG_BAR0 + g, nact * 32, p.cg_maxit, xc);
+                const uint32_t flag = Dblk + 128u + (uint32_t)(my_rows & 1) * 4u;
+                if (t == 0) sts1(flag, products >= 0 ? 1.0f : 0.0f);
+                if (prof) { cg_rows += products >= 0; cg_products += products >= 0 ? products : p.cg_maxit + 1; }
+                tc_fence_before();
+                named_bar(bar_id, GROUP);
+                if (lds1(flag) != 0.0f) {
+                    mbar_arrive(bar_acc_empty(g));   // the Gram of this group's next row may start
+                    xout[t] = t < f8 ? xc : 0.0f;
+                    if (prof) t_fact += clock64() - tt;
+                    continue;
+                }
                 tc_fence_after();
             }
 #pragma unroll 1
@@ -843,7 +877,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         if (prof) {
             p.prof[16] = clock64() - t_start; p.prof[17] = t_accfull; p.prof[18] = t_fact; p.prof[19] = t_back;
             p.prof[22] = my_rows; p.prof[24] = ph_wait; p.prof[25] = ph_ld; p.prof[26] = ph_own; p.prof[28] = ph_p;
-            p.prof[31] = ph_issue;
+            p.prof[31] = ph_issue; p.prof[32] = cg_rows; p.prof[33] = cg_products;
         }
     }
     // =============================== TEARDOWN ===============================

@@ -19,6 +19,7 @@
 #include "tc_common.cuh"
 #include "half_step.cuh"
 #include "factor8.cuh"
+#include "cg_solve.cuh"
 
 namespace wmf {
 
@@ -133,21 +134,28 @@ als_half_step_tc256_kernel(HalfStepParams p, const int4* __restrict__ rowtab, co
                 if (e.n > 0) { cu_n = e.n; cu_lo = e.lo; cu_nsub = (e.n + SUB - 1) / SUB; cu_S = exp2f((float)e.sexp); }
             }
         };
+        // Loads only: nothing in load_raw may depend on their results (a dependent instruction there parks the warp on
+        // the full global-load latency in every step, see half_step_tc.cu). issue() finishes the record one step later:
+        // sq holds the raw weight and dp1 the row's scale until then.
         auto load_raw = [&]() {
-            Raw rw{-1, 0.f, 0.f};
+            Raw rw{-1, 0.f, cu_S};
             if (cu_k < nslots) {
                 const int off = cu_c * SUB + lane;
                 if (off < cu_n) {
-                    float d = __ldg(p.data + cu_lo + off);
+                    rw.sq = __ldg(p.data + cu_lo + off);
                     rw.idx = __ldg(p.indices + cu_lo + off);
-                    if (p.bias) d = __fsub_rn(d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
-                    rw.sq = cu_S * sqrtf(d);
-                    rw.dp1 = __fadd_rn(d, 1.0f);
                 }
             }
             return rw;
         };
-        auto issue = [&](const Raw& rw, int buf) {  // this warp's 8 rows of the sub-chunk -> raw buffer
+        auto issue = [&](Raw& rw, int buf) {  // this warp's 8 rows of the sub-chunk -> raw buffer
+            {
+                float d = rw.sq;
+                const float S = rw.dp1;
+                if (p.bias && rw.idx >= 0) d = __fsub_rn(d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
+                rw.sq = rw.idx >= 0 ? S * sqrtf(d) : 0.0f;
+                rw.dp1 = rw.idx >= 0 ? __fadd_rn(d, 1.0f) : 0.0f;
+            }
             __syncwarp();
             const uint32_t dst0 = smem_base + OFF_STG + (gw * NSTG + buf) * WSTG_BYTES + lane * 16;
 #pragma unroll
@@ -335,6 +343,19 @@ als_half_step_tc256_kernel(HalfStepParams p, const int4* __restrict__ rowtab, co
                 tc_fence_before();
                 named_bar(1, SOLVERS);
                 tc_fence_after();
+            }
+            // ---- default solver: conjugate gradients against the matrix in tensor memory (cg_solve.cuh; all eight
+            // warps hold rows, so every thread sees the same outcome); the block Gauss-Jordan below takes the rows that
+            // have not converged within p.cg_maxit products
+            if (p.cg_maxit > 0) {
+                float xc = 0.0f;
+                const int products = cg_solve(t_row, t, f16, bt, inv_s2, bfin, Dblk, warp, SOLVERS / 32, 2, SOLVERS, p.cg_maxit, xc);
+                if (products >= 0) {
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty);   // the Gram of the next row may start
+                    xout[t] = t < f8 ? xc : 0.0f;
+                    continue;
+                }
             }
 #pragma unroll 1
             for (int c0 = 0; c0 < f8; c0 += NB) {

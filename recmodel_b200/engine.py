@@ -97,8 +97,14 @@ def _h2d(arr, dtype, device):
     buf, busy = ent
     if busy is not None:
         busy.synchronize()  # the previous transfer out of this staging buffer has finished
-    _host_copy(buf[:n], t.reshape(-1))
-    out = buf[:n].to(device, non_blocking=True)
+    # chunk by chunk: the DMA of a chunk runs while the host copies the next one into the staging buffer
+    out = torch.empty(n, dtype=t.dtype, device=device)
+    flat = t.reshape(-1)
+    chunk = 4 << 20
+    for off in range(0, n, chunk):
+        end = min(n, off + chunk)
+        _host_copy(buf[off:end], flat[off:end])
+        out[off:end].copy_(buf[off:end], non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(device))
     ent[1] = ev

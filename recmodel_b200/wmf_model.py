@@ -22,7 +22,8 @@ from . import _lib, engine, sharding
 from .base_model import RecModel
 from .engine import DeviceCSR
 
-_ALGOS = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tcgen05": _lib.ALGO_TCGEN05}
+_ALGOS = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tcgen05": _lib.ALGO_TCGEN05,
+          "tcgen05_direct": _lib.ALGO_TCGEN05_DIRECT}
 
 
 class WMF(RecModel):

@@ -28,6 +28,7 @@ def run(csr, Yd, name):
     print("  gather phases: issue", f(prof[11]), "wait_stg", f(prof[5]), "xform", f(prof[12]), "arrive", f(prof[13]))
     print("  solver phases (thread 0 of group 0): wait_mma", f(prof[24]), "tmem_ld", f(prof[25]), "own_factor(4 of 16 panels)", f(prof[26]),
           "barA", f(prof[27]), "P", f(prof[28]), "split+sts+fence", f(prof[29]), "barB", f(prof[30]), "mma_issue", f(prof[31]))
+    print("  cg: rows solved", prof[32], "of", prof[22], " products", prof[33])
     return X
 U = run(Cd, Y, "user half-step")
 run(CT, U, "item half-step")

@@ -18,7 +18,10 @@ from recmodel_b200.synthetic import make_counts, make_counts_cached, split_train
 pytestmark = pytest.mark.gpu
 
 HALF_STEP_TOL = 1e-4
-ALGOS = [("simt", _lib.ALGO_SIMT), ("tcgen05", _lib.ALGO_TCGEN05)]
+# "tcgen05": conjugate gradients on the matrix in tensor memory (the product); "tcgen05_direct": the same pipeline with
+# every system factorised in tensor memory (the fallback of the former, kept tested on its own)
+ALGOS = [("simt", _lib.ALGO_SIMT), ("tcgen05", _lib.ALGO_TCGEN05), ("tcgen05_direct", _lib.ALGO_TCGEN05_DIRECT)]
+TC_ALGOS = (_lib.ALGO_TCGEN05, _lib.ALGO_TCGEN05_DIRECT)
 
 
 def dev(a, cuda_device):
@@ -47,7 +50,7 @@ def check_half_step(case, algo_name, X, ref32, x64, steady=False):
     max(1e-4, 2 x noise)."""
     noise = row_rel_err(ref32, x64)
     err32, err64 = row_rel_err(X, ref32), row_rel_err(X, x64)
-    if algo_name == "tcgen05":
+    if algo_name.startswith("tcgen05"):
         tol64, tol32 = HALF_STEP_TOL, max(HALF_STEP_TOL, 1.5 * noise)
     else:
         tol64 = tol32 = HALF_STEP_TOL if steady else max(HALF_STEP_TOL, 2.0 * noise)
@@ -162,7 +165,7 @@ def test_transpose_unsorted_duplicates_and_canonical(cuda_device):
 @pytest.mark.parametrize("name,dim,bias,mode", WEIGHTED_CASES)
 def test_half_step_vs_reference_golden(cuda_device, name, dim, bias, mode, algo_name, algo):
     f = dim + 1 if bias else dim
-    if algo == _lib.ALGO_TCGEN05 and not tc_supported(f, bias):
+    if algo in TC_ALGOS and not tc_supported(f, bias):
         pytest.skip("shape not taken by the tcgen05 path")
     g = load_golden(name)
     C = csr_from(g, "train")
@@ -185,7 +188,7 @@ def test_half_step_vs_reference_golden(cuda_device, name, dim, bias, mode, algo_
 ])
 def test_half_step_vs_oracle_realistic(cuda_device, users, items, nnz, dim, bias, algo_name, algo):
     f = dim + 1 if bias else dim
-    if algo == _lib.ALGO_TCGEN05 and not tc_supported(f, bias):
+    if algo in TC_ALGOS and not tc_supported(f, bias):
         pytest.skip("shape not taken by the tcgen05 path")
     C = make_counts_cached(users, items, nnz, seed=31)
     C.data = orc.preprocess_counts(C.data)
@@ -215,7 +218,7 @@ def test_half_step_vs_oracle_realistic(cuda_device, users, items, nnz, dim, bias
 def test_half_step_edge_rows(cuda_device, f, bias, algo_name, algo):
     """Empty rows, 1-entry rows, a row much longer than f, unsorted column order, explicit zero
     weights (SURVEY.md §4 unit level)."""
-    if algo == _lib.ALGO_TCGEN05 and not tc_supported(f, bias):
+    if algo in TC_ALGOS and not tc_supported(f, bias):
         pytest.skip("shape not taken by the tcgen05 path")
     rng = np.random.default_rng(f)
     N = 900
@@ -240,7 +243,7 @@ def test_half_step_edge_rows(cuda_device, f, bias, algo_name, algo):
 @pytest.mark.parametrize("algo_name,algo", ALGOS)
 def test_half_step_indefinite_falls_back_to_lu(cuda_device, algo_name, algo):
     """Negative confidence weights make A indefinite; the reference's sgesv still solves it."""
-    if algo == _lib.ALGO_TCGEN05 and not tc_supported(64, False):
+    if algo in TC_ALGOS and not tc_supported(64, False):
         pytest.skip("shape not taken by the tcgen05 path")
     rng = np.random.default_rng(5)
     N, f = 400, 64
@@ -255,7 +258,7 @@ def test_half_step_indefinite_falls_back_to_lu(cuda_device, algo_name, algo):
     ledger_add("indefinite_negative_weights/f64", algo_name, err_vs_ref32=row_rel_err(X, ref), err_vs_fp64=err,
                ref_noise=row_rel_err(ref, x64), tol_vs_fp64=max(tol, 1e-3), tol_vs_ref32=None)
     assert err < max(tol, 1e-3)  # indefinite systems: conditioning-limited (LU kernel on both paths)
-    if algo == _lib.ALGO_TCGEN05:  # every row with entries went through the per-row fix-up list, none through a redo
+    if algo in TC_ALGOS:  # every row with entries went through the per-row fix-up list, none through a redo
         flags, fixed = engine.half_step_status()
         assert fixed == int((np.diff(C.indptr) > 0).sum()) and (flags & 2) == 0
 
