@@ -24,12 +24,13 @@
 // own one accumulator, so while one row is in its pivot chain three others fill the issue slots.
 // One persistent CTA per SM, warp-specialised, all hand-offs through mbarriers:
 //   warps 0-15  solve    group g = warp/4 owns accumulator g and the rows n with n % 4 == g.
-//   warps 16-23 gather   two teams of 128 threads; a team takes every other 32-entry sub-chunk of a
-//               row. Thread m owns feature m: the 32 gathered factor rows land in a raw staging buffer
-//               with cp.async (one coalesced 512-B row per warp instruction, two sub-chunks in flight per
-//               warp, six operand stages ahead of the MMAs), thread m reads column m, scales, splits to FP16 hi/lo and stores
-//               the K-major swizzled operand tiles a TMA load would have produced (TMA cannot: the
-//               operand is gathered, scaled and split); the rhs partial b[m] stays in registers.
+//   warps 25-26 gather   one TMA producer warp per team: the 32 gathered factor rows of a sub-chunk land in a raw
+//               staging buffer by eight cp.async.bulk.tensor ... tile::gather4 (TMA row gather, four 512-B rows per
+//               instruction, completion on the buffer's mbarrier), two or three sub-chunks in flight per team
+//   warps 16-23 transform two teams of 128 threads; a team takes every other 32-entry sub-chunk of a row. Thread m
+//               owns feature m: it reads column m of the raw rows, scales, splits to FP16 hi/lo and stores the
+//               K-major swizzled operand tiles a tiled TMA load would have produced (TMA cannot: the operand is
+//               gathered, scaled and split); the rhs partial b[m] stays in registers.
 //   warp 24     MMA      one thread issues the Gram MMAs (at most two K-steps queued, so the solvers'
 //               rank-8 updates never wait behind a long burst) and commits stage/accumulator barriers.
 //
@@ -40,6 +41,7 @@
 // Rows whose weights are negative (sqrt undefined) or whose pivot block is not positive definite
 // raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).
 #include <stdlib.h>
+#include <cuda.h>
 #include "tc_common.cuh"
 #include "half_step.cuh"
 #include "whiten.cuh"
@@ -50,10 +52,11 @@ namespace wmf {
 
 namespace tc {
 
-// operand stages / cp.async depth: 4 / 3 or 6 / 2 fit the 227 KB (a row holds its accumulator for its Gram and its
-// solve, so tiles staged ahead of a free accumulator shorten the Gram phase; the copies need less depth than that)
+// operand stages / raw staging buffers per team: 4 / 3 or 6 / 2 fit the 227 KB (a row holds its accumulator for its
+// Gram and its solve, so tiles staged ahead of a free accumulator shorten the Gram phase; the TMA row gathers want
+// their own depth: a gather is in flight for ~1400 cycles when it misses L2, scripts/probe/tma_gather4_probe.cu)
 #ifndef WMF_TC_STAGES
-#define WMF_TC_STAGES 6
+#define WMF_TC_STAGES 4
 #endif
 constexpr int STAGES = WMF_TC_STAGES, STAGING = STAGES == 4 ? 3 : 2;
 static_assert(STAGES == 4 || STAGES == 6, "operand stages");
@@ -62,18 +65,18 @@ constexpr int F = 128;               // factor width handled by this kernel
 constexpr int SUB = 32;              // stored entries per sub-chunk (one pipeline stage)
 constexpr int NSTAGE = STAGES;       // operand stages (two sub-chunks share one 128-byte-swizzled tile pair)
 constexpr int NTEAM = 2;             // gather teams
-constexpr int NSTG = STAGING;        // raw staging buffers per team (cp.async depth)
+constexpr int NSTG = STAGING;        // raw staging buffers per team (TMA gathers in flight)
 constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 64 fp16 (K) = 16 KB, holds two sub-chunks
 constexpr int PAIR_BYTES = 2 * TILE_BYTES;   // [zh ; zl]
 constexpr int STG_BYTES = SUB * F * 4;       // 32 gathered factor rows, row-major fp32, 16 KB
-constexpr int META_BYTES = SUB * 8;          // S*sqrt(d) [32] then d+1 [32], one copy per gather warp and buffer
-constexpr int WSTG_BYTES = SUB * 32 * 4;     // a gather warp's slice of a staging buffer: 32 entries x 32 features
+constexpr int META_BYTES = SUB * 8 + 16;     // per staging buffer: S*sqrt(d) [32], d+1 [32], then the sub-chunk's descriptor
 constexpr int NB = 8;                // Gauss-Jordan step width
 constexpr int NGROUP = 4;            // solver groups = TMEM accumulators
 constexpr int GROUP = 128;
 constexpr int TEAM = 128;
 constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WARP0 + NTEAM * 4;  // high warp ids issue first
-constexpr int THREADS = (MMA_WARP + 1) * 32;               // 800
+constexpr int PRODUCER_WARP0 = MMA_WARP + 1;               // one TMA producer warp per gather team
+constexpr int THREADS = (PRODUCER_WARP0 + NTEAM) * 32;     // 864
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int CG_BAR0 = 1 + NGROUP;  // named barriers 1 .. NGROUP: a whole solver group; CG_BAR0 + g: its warps that hold rows
 static_assert(NGROUP * F <= 512, "TMEM columns");
@@ -92,10 +95,10 @@ constexpr int GROUP_BYTES = ((G_OFF_BFIN + F * 4 + 127) / 128) * 128;
 constexpr int OFF_STAGES = 0;                                        // NSTAGE/2 tile pairs
 constexpr int OFF_STG = OFF_STAGES + (NSTAGE / 2) * PAIR_BYTES;
 constexpr int OFF_META = OFF_STG + NTEAM * NSTG * STG_BYTES;
-constexpr int OFF_GROUPS = ((OFF_META + NTEAM * 4 * NSTG * META_BYTES + 127) / 128) * 128;
+constexpr int OFF_GROUPS = ((OFF_META + NTEAM * NSTG * META_BYTES + 127) / 128) * 128;
 constexpr int OFF_BVEC = OFF_GROUPS + NGROUP * GROUP_BYTES;         // NGROUP x NTEAM x F floats
 constexpr int OFF_BARS = OFF_BVEC + NGROUP * NTEAM * F * 4;         // mbarriers (8 B each)
-constexpr int NBARS = 2 * NSTAGE + NTEAM * NSTG + 2 + (4 + NTEAM) * NGROUP;
+constexpr int NBARS = 2 * NSTAGE + 2 * NTEAM * NSTG + 2 + (4 + NTEAM) * NGROUP;
 constexpr int OFF_TMEM_PTR = OFF_BARS + NBARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                // + slack for alignment
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -298,17 +301,18 @@ using namespace tc;
 
 template <bool PROF>
 __global__ void __launch_bounds__(THREADS, 1)
-als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const int4* __restrict__ segtab,
-                        float* __restrict__ parts, int* __restrict__ counters, const uint32_t* __restrict__ hdr_u,
-                        int64_t extra_slot0, int* __restrict__ flags) {
+als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams p, const int4* __restrict__ rowtab,
+                        const int4* __restrict__ segtab, float* __restrict__ parts, int* __restrict__ counters,
+                        const uint32_t* __restrict__ hdr_u, int64_t extra_slot0, int* __restrict__ flags) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = smem_base + OFF_BARS;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
-    auto bar_stg = [&](int team, int s) { return bars + 8u * (2 * NSTAGE + team * NSTG + s); };
-    auto bar_thr = [&](int x) { return bars + 8u * (2 * NSTAGE + NTEAM * NSTG + x); };
-    constexpr int B0 = 2 * NSTAGE + NTEAM * NSTG + 2;
+    auto bar_stg_full = [&](int team, int s) { return bars + 8u * (2 * NSTAGE + team * NSTG + s); };
+    auto bar_stg_empty = [&](int team, int s) { return bars + 8u * (2 * NSTAGE + NTEAM * NSTG + team * NSTG + s); };
+    auto bar_thr = [&](int x) { return bars + 8u * (2 * NSTAGE + 2 * NTEAM * NSTG + x); };
+    constexpr int B0 = 2 * NSTAGE + 2 * NTEAM * NSTG + 2;
     auto bar_acc_full = [&](int g) { return bars + 8u * (B0 + g); };
     auto bar_acc_empty = [&](int g) { return bars + 8u * (B0 + NGROUP + g); };
     auto bar_b_empty = [&](int g) { return bars + 8u * (B0 + 2 * NGROUP + g); };
@@ -319,7 +323,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), TEAM); mbar_init(bar_empty(s), 1); }
-        for (int s = 0; s < NTEAM * NSTG; ++s) mbar_init(bar_stg(0, s), TEAM);
+        for (int s = 0; s < NTEAM * NSTG; ++s) { mbar_init(bar_stg_full(0, s), 1); mbar_init(bar_stg_empty(0, s), 4); }
         mbar_init(bar_thr(0), 1);
         mbar_init(bar_thr(1), 1);
         for (int g = 0; g < NGROUP; ++g) {
@@ -363,15 +367,17 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
         return e;
     };
 
-    if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
-        // =============================== GATHER ===============================
-        // Team T walks the rows of this CTA and takes the sub-chunks c with (c + row_n + T) even. Three
-        // of its sub-chunks are in flight: j+3 index/weight -> registers (lanes 0-7 of each warp), j+2
-        // factor rows -> raw staging buffer (cp.async), j -> operand tiles.
-        const int team = (warp - GATHER_WARP0) >> 2;
-        const int m = (tid - GATHER_WARP0 * 32) & (TEAM - 1);  // feature index
-        const int gw = (warp - GATHER_WARP0) & 3;              // warp within the team
-        // cursor: the team's next sub-chunk, NSTG steps ahead of the transform
+    if (warp >= PRODUCER_WARP0) {
+        // =============================== GATHER: TMA PRODUCER ===============================
+        // One warp per team. It walks the rows of this CTA, takes the sub-chunks c with (c + row_n + T) even and, for
+        // each, has the 32 gathered factor rows copied into one of the team's raw staging buffers by the TMA unit:
+        // eight cp.async.bulk.tensor ... tile::gather4 (four rows of 512 B each, lanes 0-7 issue one apiece) that
+        // complete on the buffer's mbarrier. Beside the rows it leaves the per-entry scales S*sqrt(d), d+1 and a
+        // descriptor (global sub-chunk index, row, last-of-row flag), so the eight transform warps run no cursor,
+        // address or copy code at all. Entry indices and weights are loaded one step ahead; nothing may depend on
+        // those loads in the step that issues them (a dependent instruction there parks the warp on the full
+        // global-load latency every step).
+        const int team = warp - PRODUCER_WARP0;
         int cu_k = -1;        // CTA-local slot of the current row
         int cu_row_n = -1;    // index of the row among this CTA's non-empty rows
         int cu_c = 0, cu_nsub = 0, cu_n = 0, cu_gi0 = 0;  // sub-chunk in row, sub-chunks / entries of the row, global index of sub-chunk 0
@@ -399,98 +405,89 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 cu_c = (team + cu_row_n) & 1;
             }
         };
-        struct Desc {  // what the later pipeline steps need to know about a sub-chunk
-            int gi;       // global sub-chunk index (-1: none)
-            int row_n;
-            bool last;    // the team's last sub-chunk of its row: deliver the rhs partial
-        };
-        auto describe = [&]() -> Desc {
-            if (cu_k >= nslots) return Desc{-1, 0, false};
-            return Desc{cu_gi0 + cu_c, cu_row_n, cu_c + 2 >= cu_nsub};
-        };
-        // Every gather warp is its own pipeline: it stages the 32-feature slice (128 B) of the 32 factor rows that
-        // its lanes will read, so nothing but the operand-stage barriers is shared inside a team.
-        struct Raw { int idx; float d; float s; };
-        const int wbuf0 = ((team * 4 + gw) * NSTG);  // this warp's first staging / meta buffer
+        struct Raw { int idx; float d; float s; int gi; int row_n; int last; };
         auto load_raw = [&]() {  // lane l: entry l of the cursor's sub-chunk
-            Raw rw{-1, 0.f, cu_S};
+            Raw rw{-1, 0.f, cu_S, -1, 0, 0};
             if (cu_k < nslots) {
+                rw.gi = cu_gi0 + cu_c; rw.row_n = cu_row_n; rw.last = cu_c + 2 >= cu_nsub ? 1 : 0;
                 const int off = cu_c * SUB + lane;
                 if (off < cu_n) {
-                    // Loads only: nothing here may depend on their results. They are first touched one pipeline step
-                    // later (issue()); a dependent instruction placed here (the bias look-up used to be) parks the warp
-                    // on the full global-load latency in every step, whether or not its predicate is set (ncu: half
-                    // of the gather warps' time).
-                    rw.d = __ldg(p.data + cu_lo + off);
+                    rw.d = __ldg(p.data + cu_lo + off);      // loads only (see above)
                     rw.idx = __ldg(p.indices + cu_lo + off);
                 }
             }
             return rw;
         };
-        auto issue = [&](Raw rw, int buf) {
-            const int wb = wbuf0 + buf;
+        const int oob_row = (int)p.cols;   // a row index past the tensor: the TMA unit fills zeros (padding entries)
+        advance(true);
+        Raw nx = load_raw();
+        uint32_t jp = 0;
+        for (;;) {
+            Raw rw = nx;
+            if (rw.gi >= 0) { advance(false); nx = load_raw(); }
+            const int buf = (int)(jp % NSTG);
+            mbar_wait(bar_stg_empty(team, buf), ((jp / NSTG) & 1u) ^ 1u);   // the transform warps have read it
+            const uint32_t mt = smem_base + OFF_META + (team * NSTG + buf) * META_BYTES;
+            if (rw.gi < 0) {   // no more sub-chunks: leave the terminator
+                if (lane == 0) { sts4u(mt + SUB * 8, 0xffffffffu, 0u, 0u, 0u); mbar_arrive(bar_stg_full(team, buf)); }
+                break;
+            }
             if (p.bias && rw.idx >= 0) rw.d = __fsub_rn(rw.d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
-            __syncwarp();  // the buffer's previous contents have been read by every lane
             {
                 float sq = 0.f, dp1 = 0.f;
                 if (rw.idx >= 0) {  // rows with a negative weight never get here (fix-up list, tc_prep_rows_kernel)
                     sq = rw.s * sqrtf(rw.d);
                     dp1 = __fadd_rn(rw.d, 1.0f);
                 }
-                const uint32_t ma = smem_base + OFF_META + wb * META_BYTES + lane * 4;
-                sts1(ma, sq);
-                sts1(ma + SUB * 4, dp1);
+                sts1(mt + lane * 4, sq);
+                sts1(mt + SUB * 4 + lane * 4, dp1);
+                if (lane == 0) sts4u(mt + SUB * 8, (uint32_t)rw.gi, (uint32_t)rw.row_n, (uint32_t)rw.last, 0u);
             }
-            // one instruction copies the 128-B slices of four entries: lanes 8k..8k+7 take entry 4i + k
-            const uint32_t dst0 = smem_base + OFF_STG + wb * WSTG_BYTES + (lane >> 3) * 128 + (lane & 7) * 16;
-            const int64_t col = gw * 32 + (lane & 7) * 4;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = __shfl_sync(0xffffffffu, rw.idx, 4 * i + (lane >> 3));
-                const float* src = p.Y + (int64_t)(idx >= 0 ? idx : 0) * p.ldy + col;
-                cp_async16(dst0 + i * 512, src, idx >= 0 ? 16u : 0u);  // size 0 -> zero fill
+            const int vi = rw.idx >= 0 ? rw.idx : oob_row;
+            const int i0 = __shfl_sync(0xffffffffu, vi, (4 * lane) & 31), i1 = __shfl_sync(0xffffffffu, vi, (4 * lane + 1) & 31);
+            const int i2 = __shfl_sync(0xffffffffu, vi, (4 * lane + 2) & 31), i3 = __shfl_sync(0xffffffffu, vi, (4 * lane + 3) & 31);
+            __syncwarp();   // every lane's scales are written before lane 0's release below
+            const uint32_t fb = bar_stg_full(team, buf);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)STG_BYTES) : "memory");
+            if (lane < SUB / 4) {
+                const uint32_t dst = smem_base + OFF_STG + (team * NSTG + buf) * STG_BYTES + lane * (4 * F * 4);
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+                    " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&ymap)), "r"(fb),
+                    "r"(0), "r"(i0), "r"(i1), "r"(i2), "r"(i3) : "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        advance(true);
-        Desc d0 = describe();
-        issue(load_raw(), 0);
-        advance(false);
-        Desc d1 = describe();
-        Desc d2{-1, 0, false};
-        Raw r2;
-        if constexpr (NSTG == 3) {
-            issue(load_raw(), 1);
-            advance(false);
-            d2 = describe();
-            r2 = load_raw();
-            advance(false);
-        } else {
-            r2 = load_raw();
-            advance(false);
+            ++jp;
         }
-        // in iteration j the copy groups of sub-chunks j .. j+NSTG-1 are in flight: wait_group NSTG-1 completes j
+    } else if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
+        // =============================== GATHER: TRANSFORM ===============================
+        // Two teams of 128 threads; thread m owns feature m. A team takes the staging buffers its producer warp fills
+        // in order: thread m reads column m of the 32 raw rows, scales, splits to FP16 hi/lo and stores the K-major
+        // swizzled operand tiles a tiled TMA load would have produced (TMA cannot: the operand is gathered, scaled and
+        // split); the rhs partial b[m] stays in registers until the row's last sub-chunk of the team.
+        const int team = (warp - GATHER_WARP0) >> 2;
+        const int m = (tid - GATHER_WARP0 * 32) & (TEAM - 1);  // feature index
         uint32_t j = 0;
         double bacc = 0.0;
         const bool prof = PROF && blockIdx.x == 0 && m == 0 && team == 0;
-        long long t_empty = 0, t_bempty = 0, t_stg = 0, t_issue = 0, t_xform = 0, t_start = prof ? clock64() : 0, tt = 0, t2 = 0;
-        while (d0.gi >= 0) {
+        long long t_empty = 0, t_bempty = 0, t_stg = 0, t_xform = 0, t_start = prof ? clock64() : 0, tt = 0, t2 = 0;
+        for (;;) {
+            const int sb = (int)(j % NSTG);
             if (prof) t2 = clock64();
-            const Desc d3 = describe();
-            if constexpr (NSTG == 3) issue(r2, (j + 2) % 3);   // sub-chunk j+2
-            else issue(r2, (j + 1) & 1);                         // sub-chunk j+1
-            r2 = load_raw();             // the sub-chunk after that, first touched next iteration
-            advance(false);
-            const int s = d0.gi % NSTAGE, sb = j % NSTG;
-            if (prof) { tt = clock64(); t_issue += tt - t2; }
-            if constexpr (NSTG == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");  // this warp's copies for sub-chunk j have landed
-            else asm volatile("cp.async.wait_group 1;" ::: "memory");
-            __syncwarp();
-            if (prof) { t2 = clock64(); t_stg += t2 - tt; }
-            mbar_wait(bar_empty(s), (((uint32_t)d0.gi / NSTAGE) & 1u) ^ 1u);
-            if (prof) { tt = clock64(); t_empty += tt - t2; }
-            const uint32_t stg = smem_base + OFF_STG + (wbuf0 + sb) * WSTG_BYTES + lane * 4;
-            const uint32_t mt = smem_base + OFF_META + (wbuf0 + sb) * META_BYTES;
+            mbar_wait(bar_stg_full(team, sb), (j / NSTG) & 1u);   // rows (async proxy) and scales (producer warp) have landed
+            if (prof) { tt = clock64(); t_stg += tt - t2; }
+            const uint32_t stg = smem_base + OFF_STG + (team * NSTG + sb) * STG_BYTES + m * 4;
+            const uint32_t mt = smem_base + OFF_META + (team * NSTG + sb) * META_BYTES;
+            int d_gi, d_row_n, d_last;
+            {
+                uint32_t a, b, c, d;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(mt + SUB * 8));
+                d_gi = (int)a; d_row_n = (int)b; d_last = (int)c;
+            }
+            if (d_gi < 0) break;
+            const int s = d_gi % NSTAGE;
+            mbar_wait(bar_empty(s), (((uint32_t)d_gi / NSTAGE) & 1u) ^ 1u);
+            if (prof) { t2 = clock64(); t_empty += t2 - tt; tt = t2; }
             const uint32_t tile_h = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + m * 128;
             const int half = s & 1;
             float part = 0.f;
@@ -504,7 +501,7 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 sqn[0] = sa.x; sqn[1] = sa.y; sqn[2] = sa.z; sqn[3] = sa.w; sqn[4] = sb4.x; sqn[5] = sb4.y; sqn[6] = sb4.z; sqn[7] = sb4.w;
                 dpn[0] = da.x; dpn[1] = da.y; dpn[2] = da.z; dpn[3] = da.w; dpn[4] = db.x; dpn[5] = db.y; dpn[6] = db.z; dpn[7] = db.w;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) vn[e] = lds1(stg + (c * 8 + e) * 128);
+                for (int e = 0; e < 8; ++e) vn[e] = lds1(stg + (c * 8 + e) * (F * 4));
             };
             load_chunk(0);
 #pragma unroll
@@ -533,10 +530,12 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
             bacc += (double)part;
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full(s));
+            __syncwarp();        // every lane has read the raw rows and scales: the producer may refill the buffer
+            if (lane == 0) mbar_arrive(bar_stg_empty(team, sb));
             if (prof) { t2 = clock64(); t_xform += t2 - tt; }
-            if (d0.last) {  // hand the team's rhs partial to the solver group that owns this row
-                const int g = d0.row_n % NGROUP;
-                const uint32_t bph = ((uint32_t)d0.row_n / NGROUP) & 1u;
+            if (d_last) {  // hand the team's rhs partial to the solver group that owns this row
+                const int g = d_row_n % NGROUP;
+                const uint32_t bph = ((uint32_t)d_row_n / NGROUP) & 1u;
                 mbar_wait(bar_b_empty(g), bph ^ 1u);
                 sts1(smem_base + OFF_BVEC + ((g * NTEAM + team) * F + m) * 4, (float)bacc);
                 mbar_arrive(bar_b_full(g, team));
@@ -544,11 +543,8 @@ als_half_step_tc_kernel(HalfStepParams p, const int4* __restrict__ rowtab, const
                 if (prof) t_bempty += clock64() - t2;
             }
             ++j;
-            if constexpr (NSTG == 3) { d0 = d1; d1 = d2; d2 = d3; }
-            else { d0 = d1; d1 = d3; }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = j; p.prof[5] = t_stg; p.prof[11] = t_issue; p.prof[12] = t_xform; }
+        if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = j; p.prof[5] = t_stg; p.prof[12] = t_xform; }
     } else if (warp == MMA_WARP) {
         // =============================== GRAM MMA ISSUE ===============================
         if (lane == 0) {
@@ -1006,15 +1002,27 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
         rc = tc256_launch(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags, grid, st);
         if (rc) return rc;
     } else {
+        // TMA descriptor of the whitened factors Y~ [cols x 128] for the row gathers (tile::gather4: one 512-byte row
+        // per box, four row indices per instruction; rows past `cols` read as zeros)
+        CUtensorMap ymap;
+        {
+            const cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)(in.cols > 0 ? in.cols : 1)};
+            const cuuint64_t gstride[1] = {(cuuint64_t)F * sizeof(float)};
+            const cuuint32_t box[2] = {(cuuint32_t)F, 1u}, estr[2] = {1u, 1u};
+            const CUresult cr = cuTensorMapEncodeTiled(&ymap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Yt, gdim, gstride, box, estr,
+                                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { set_error("wmf_als_half_step(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)cr); return WMF_ERR_CUDA; }
+        }
         // the attribute is per device: set it on every call (a process may drive several GPUs)
         if (p.prof) {
 #ifdef WMF_TC_PROFILE_BUILD
             WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
+            als_half_step_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(ymap, p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
 #endif
         } else {
             WMF_CUDA(cudaFuncSetAttribute(als_half_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-            als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
+            als_half_step_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(ymap, p, tab, segtab, parts, counters, hdr_u, extra_slot0, flags);
         }
         WMF_LAUNCH_CHECK("als_half_step_tc_kernel");
     }
