@@ -200,7 +200,8 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
         }
     } else if (warp == MMA_WARP) {
         // =============================== GRAM MMA ISSUE ===============================
-        if (lane == 0) {
+        // warp-uniform loop, one elected lane issues (see elect_one())
+        {
             uint32_t gsi = 0, row_n = 0;
             RowEnt nxt = ent_at(0);
             for (int k = 0; k < nslots; ++k) {
@@ -220,17 +221,21 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                     tc_fence_after();
                     const uint32_t tile = smem_base + OFF_STAGES + s * PAIR_BYTES;
                     const uint64_t dh = umma_desc(tile), dl = umma_desc(tile + TILE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {   // 16 fp16 features = 32 B along K inside the 128-B swizzle row
-                        const uint64_t hk = dh + (uint64_t)(kk * 2), lk = dl + (uint64_t)(kk * 2);
-                        umma_f16(d_tmem, hk, hk, idesc, accumulate);  // wh wh^T
-                        umma_f16(d_tmem, hk, lk, idesc, 1u);          // wh wl^T
-                        umma_f16(d_tmem, lk, hk, idesc, 1u);          // wl wh^T
-                        accumulate = 1;
+                        for (int kk = 0; kk < 4; ++kk) {   // 16 fp16 features = 32 B along K inside the 128-B swizzle row
+                            const uint64_t hk = dh + (uint64_t)(kk * 2), lk = dl + (uint64_t)(kk * 2);
+                            umma_f16(d_tmem, hk, hk, idesc, kk == 0 ? accumulate : 1u);  // wh wh^T
+                            umma_f16(d_tmem, hk, lk, idesc, 1u);          // wh wl^T
+                            umma_f16(d_tmem, lk, hk, idesc, 1u);          // wl wh^T
+                        }
+                        tc_commit(bar_empty(s));
                     }
-                    tc_commit(bar_empty(s));
+                    __syncwarp();
+                    accumulate = 1;
                 }
-                tc_commit(bar_acc_full(g));
+                if (elect_one()) tc_commit(bar_acc_full(g));
+                __syncwarp();
                 ++row_n;
             }
         }

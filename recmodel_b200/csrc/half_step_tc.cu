@@ -547,9 +547,11 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
         if (prof) { p.prof[0] = clock64() - t_start; p.prof[1] = t_empty; p.prof[2] = t_bempty; p.prof[3] = j; p.prof[5] = t_stg; p.prof[12] = t_xform; }
     } else if (warp == MMA_WARP) {
         // =============================== GRAM MMA ISSUE ===============================
-        if (lane == 0) {
+        // The whole warp runs the (warp-uniform) loop and waits on the barriers; one elected lane issues the MMAs and
+        // the commits (see elect_one()).
+        {
             uint32_t gi = 0, row_n = 0;
-            const bool prof = PROF && blockIdx.x == 0;
+            const bool prof = PROF && blockIdx.x == 0 && lane == 0;
             long long t_full = 0, t_accempty = 0, t_thr = 0, t_start = prof ? clock64() : 0, tt = 0;
             RowEnt nxt = ent_at(0);
             for (int k = 0; k < nslots; ++k) {
@@ -572,25 +574,30 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
                     if (prof) t_full += clock64() - tt;
                     tc_fence_after();
                     const int kc = (e.n - base) < SUB ? (e.n - base) : SUB;
-                    const int nk = (kc + 15) >> 4;
                     const uint32_t tile = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + (s & 1) * 64;
                     const uint64_t dh = umma_desc(tile), dl = umma_desc(tile + TILE_BYTES);
-                    if (gi >= 2) {  // at most two sub-chunks (12 MMAs) queued ahead of the solvers' updates
+                    if (p.cg_maxit == 0 && gi >= 2) {  // factorisation only: at most two sub-chunks (12 MMAs) queued ahead of the solvers' rank-8 updates
                         if (prof) tt = clock64();
                         mbar_wait(bar_empty((gi - 2) % NSTAGE), ((gi - 2) / NSTAGE) & 1u);
                         if (prof) t_thr += clock64() - tt;
                     }
-                    for (int kk = 0; kk < nk; ++kk) {
-                        // advance 16 fp16 = 32 B along K inside the 128-B swizzle row
-                        const uint64_t hk = dh + (uint64_t)(kk * 2), lk = dl + (uint64_t)(kk * 2);
-                        umma_f16(d_tmem, hk, hk, idesc_gram, accumulate);  // zh zh^T
-                        umma_f16(d_tmem, hk, lk, idesc_gram, 1u);          // zh zl^T
-                        umma_f16(d_tmem, lk, hk, idesc_gram, 1u);          // zl zh^T
-                        accumulate = 1;
+                    if (elect_one()) {
+                        // 16 fp16 = 32 B along K inside the 128-B swizzle row per K-step; a sub-chunk is one or two of them
+                        umma_f16(d_tmem, dh, dh, idesc_gram, accumulate);  // zh zh^T
+                        umma_f16(d_tmem, dh, dl, idesc_gram, 1u);          // zh zl^T
+                        umma_f16(d_tmem, dl, dh, idesc_gram, 1u);          // zl zh^T
+                        if (kc > 16) {
+                            umma_f16(d_tmem, dh + 2, dh + 2, idesc_gram, 1u);
+                            umma_f16(d_tmem, dh + 2, dl + 2, idesc_gram, 1u);
+                            umma_f16(d_tmem, dl + 2, dh + 2, idesc_gram, 1u);
+                        }
+                        tc_commit(bar_empty(s));
                     }
-                    tc_commit(bar_empty(s));
+                    __syncwarp();
+                    accumulate = 1;
                 }
-                tc_commit(bar_acc_full(g));
+                if (elect_one()) tc_commit(bar_acc_full(g));
+                __syncwarp();
                 ++row_n;
             }
             if (prof) { p.prof[8] = clock64() - t_start; p.prof[9] = t_full; p.prof[10] = t_accempty; p.prof[13] = t_thr; }

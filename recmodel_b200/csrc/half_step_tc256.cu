@@ -236,7 +236,8 @@ als_half_step_tc256_kernel(HalfStepParams p, const int4* __restrict__ rowtab, co
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp == MMA_WARP) {
         // =============================== GRAM MMA ISSUE ===============================
-        if (lane == 0) {
+        // warp-uniform loop, one elected lane issues (see elect_one())
+        {
             uint32_t gi = 0, row_n = 0;
             const uint32_t idesc = IDESC_F16_M128 | IDESC_MN_MAJOR_AB | ((uint32_t)(f16 >> 3) << 17);  // N = live columns
             RowEnt nxt = ent_at(0);
@@ -254,23 +255,27 @@ als_half_step_tc256_kernel(HalfStepParams p, const int4* __restrict__ rowtab, co
                     const int kc = (e.n - base) < SUB ? (e.n - base) : SUB;
                     const int nk = (kc + 15) >> 4;
                     const uint32_t tile = smem_base + OFF_STAGES + s * PAIR_BYTES;
-                    for (int kk = 0; kk < nk; ++kk) {   // 16 entries = two 8-entry K groups
-                        const uint32_t th = tile + kk * 2 * TILE_SBO, tl = th + TILE_BYTES;
-                        const uint64_t bh = umma_desc_mn(th, TILE_LBO, TILE_SBO), bl = umma_desc_mn(tl, TILE_LBO, TILE_SBO);
+                    if (elect_one()) {
+                        for (int kk = 0; kk < nk; ++kk) {   // 16 entries = two 8-entry K groups
+                            const uint32_t th = tile + kk * 2 * TILE_SBO, tl = th + TILE_BYTES;
+                            const uint64_t bh = umma_desc_mn(th, TILE_LBO, TILE_SBO), bl = umma_desc_mn(tl, TILE_LBO, TILE_SBO);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {   // matrix rows 128 h .. 128 h + 127 = feature blocks 2h, 2h + 1
-                            const uint64_t ah = umma_desc_mn(th + 2 * h * TILE_LBO, TILE_LBO, TILE_SBO);
-                            const uint64_t al = umma_desc_mn(tl + 2 * h * TILE_LBO, TILE_LBO, TILE_SBO);
-                            const uint32_t d = tmem_base + (uint32_t)(h * F);
-                            umma_f16(d, ah, bh, idesc, accumulate);  // zh zh^T
-                            umma_f16(d, ah, bl, idesc, 1u);          // zh zl^T
-                            umma_f16(d, al, bh, idesc, 1u);          // zl zh^T
+                            for (int h = 0; h < 2; ++h) {   // matrix rows 128 h .. 128 h + 127 = feature blocks 2h, 2h + 1
+                                const uint64_t ah = umma_desc_mn(th + 2 * h * TILE_LBO, TILE_LBO, TILE_SBO);
+                                const uint64_t al = umma_desc_mn(tl + 2 * h * TILE_LBO, TILE_LBO, TILE_SBO);
+                                const uint32_t d = tmem_base + (uint32_t)(h * F);
+                                umma_f16(d, ah, bh, idesc, kk == 0 ? accumulate : 1u);  // zh zh^T
+                                umma_f16(d, ah, bl, idesc, 1u);          // zh zl^T
+                                umma_f16(d, al, bh, idesc, 1u);          // zl zh^T
+                            }
                         }
-                        accumulate = 1;
+                        tc_commit(bar_empty(s));
                     }
-                    tc_commit(bar_empty(s));
+                    __syncwarp();
+                    accumulate = 1;
                 }
-                tc_commit(bar_acc_full);
+                if (elect_one()) tc_commit(bar_acc_full);
+                __syncwarp();
                 ++row_n;
             }
         }

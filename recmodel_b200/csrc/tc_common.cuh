@@ -68,6 +68,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 #endif
 }
+// One lane of a converged warp (always the same one for a full mask). Around tcgen05.mma / tcgen05.commit it tells the
+// compiler that exactly one thread issues them: `if (lane == 0)` makes it wrap every MMA in an ELECT / BRA.U.ANY loop
+// and move each descriptor through R2UR (~85 cycles per MMA measured, scripts/probe/step_latency.cu), while a
+// warp-uniform loop with the issue under elect.sync keeps descriptors in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
