@@ -42,6 +42,7 @@
 // raise a flag; the caller then re-runs the half-step with the SIMT kernel (LU).
 #include <stdlib.h>
 #include <cuda.h>
+#include <cudaTypedefs.h>
 #include "tc_common.cuh"
 #include "half_step.cuh"
 #include "whiten.cuh"
@@ -1016,9 +1017,20 @@ int tc_half_step(const HalfStepParams& in, void* ws, size_t ws_bytes, cudaStream
             const cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)(in.cols > 0 ? in.cols : 1)};
             const cuuint64_t gstride[1] = {(cuuint64_t)F * sizeof(float)};
             const cuuint32_t box[2] = {(cuuint32_t)F, 1u}, estr[2] = {1u, 1u};
-            const CUresult cr = cuTensorMapEncodeTiled(&ymap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Yt, gdim, gstride, box, estr,
-                                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            // the driver entry point is looked up at run time: the library must load on a machine without libcuda
+            // (the build check runs on a CPU-only box)
+            static const PFN_cuTensorMapEncodeTiled_v12000 encode = [] {
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+                    q != cudaDriverEntryPointSuccess)
+                    fn = nullptr;
+                return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+            }();
+            if (encode == nullptr) { set_error("wmf_als_half_step(tcgen05): cuTensorMapEncodeTiled is not available in this driver"); return WMF_ERR_CUDA; }
+            const CUresult cr = encode(&ymap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Yt, gdim, gstride, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (cr != CUDA_SUCCESS) { set_error("wmf_als_half_step(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)cr); return WMF_ERR_CUDA; }
         }
         // the attribute is per device: set it on every call (a process may drive several GPUs)

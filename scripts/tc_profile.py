@@ -31,4 +31,10 @@ def run(csr, Yd, name):
     print("  cg: rows solved", prof[32], "of", prof[22], " products", prof[33])
     return X
 U = run(Cd, Y, "user half-step")
-run(CT, U, "item half-step")
+V = run(CT, U, "item half-step")
+if "--steady" in sys.argv:   # a few more epochs, then the same profile with steady-state factors
+    for _ in range(3):
+        U = engine.half_step(Cd, V, engine.gram(V, 0.1), algo=_lib.ALGO_TCGEN05)
+        V = engine.half_step(CT, U, engine.gram(U, 0.1), algo=_lib.ALGO_TCGEN05)
+    U2 = run(Cd, V, "user half-step, epoch 5")
+    run(CT, U2, "item half-step, epoch 5")
