@@ -25,7 +25,7 @@ namespace wmf {
 namespace tc {
 
 // relative residual (2-norm) at which the iteration stops; the error of x is then <= cond(A) * CG_TOL
-constexpr float CG_TOL = 5.0e-7f;
+constexpr float CG_TOL = 1.0e-6f;
 constexpr float CG_TOL2 = CG_TOL * CG_TOL;
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -107,29 +107,34 @@ __device__ __forceinline__ int cg_solve(uint32_t t_row, int t, int W, float b, f
                                         int wi, int nw, int bar, int nthr, int maxit, float& x_out) {
     const bool live = t < W;
     const int lane = threadIdx.x & 31;
+    const bool solo = nw == 1;   // a single warp holds every row: no block barrier, no exchange through shared memory
     float x = 0.0f, r = live ? b : 0.0f, pv = 0.0f, sv = 0.0f;
     float gamma_old = 1.0f, alpha_old = 1.0f, gamma0 = 0.0f;
     int products = -1;
 #pragma unroll 1
     for (int it = 0;; ++it) {
         if (live) sts1(vec + (uint32_t)t * 4u, r);
-        named_bar(bar, nthr);
+        if (solo) __syncwarp(); else named_bar(bar, nthr);
         float w = fmaf(cg_row_dot(t_row, vec, W), inv_s2, r);   // (A r)_t
         w = live ? w : 0.0f;
         float g = r * r, d = r * w;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            g += __shfl_xor_sync(0xffffffffu, g, o);
+        for (int o = 16; o > 0; o >>= 1) {   // (every lane ends up with the warp's sums; the shuffles also order this
+            g += __shfl_xor_sync(0xffffffffu, g, o);   //  step's reads of `vec` before the next step's writes)
             d += __shfl_xor_sync(0xffffffffu, d, o);
         }
-        const uint32_t rb = red + (uint32_t)((it & 1) * nw) * 8u;
-        if (lane == 0) sts2(rb + (uint32_t)wi * 8u, g, d);
-        named_bar(bar, nthr);
-        float gamma = 0.0f, delta = 0.0f;
-        for (int k = 0; k < nw; ++k) {
-            const float2 q = lds2(rb + (uint32_t)k * 8u);
-            gamma += q.x;
-            delta += q.y;
+        float gamma = g, delta = d;
+        if (!solo) {
+            const uint32_t rb = red + (uint32_t)((it & 1) * nw) * 8u;
+            if (lane == 0) sts2(rb + (uint32_t)wi * 8u, g, d);
+            named_bar(bar, nthr);
+            gamma = 0.0f;
+            delta = 0.0f;
+            for (int k = 0; k < nw; ++k) {
+                const float2 q = lds2(rb + (uint32_t)k * 8u);
+                gamma += q.x;
+                delta += q.y;
+            }
         }
         if (it == 0) gamma0 = gamma;
         if (gamma <= CG_TOL2 * gamma0) { products = it + 1; break; }   // also a zero right-hand side

@@ -129,67 +129,77 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
         const int csel = lane >> 4;                 // which 64-feature chunk of a 128-feature pass this lane feeds
         const uint32_t q = (uint32_t)(lane & 15) >> 1, half8 = (uint32_t)(lane & 1) * 8u;
         uint32_t gsi = 0;                           // stages consumed so far by this CTA
-        RowEnt nxt = ent_at(0);
+        // The warp's entries of a row are j = w, w + NGATHER, ...: lane l holds entry w + NGATHER l. Their indices and
+        // weights are fetched one row ahead (nothing may depend on those loads in the step that issues them), and the
+        // factor rows are read four entries at a time with the next four already in flight: every global-load latency
+        // of a row used to be exposed once per row / per four entries, which made the gather the critical path of
+        // this kernel.
+        struct Pre { int idx; float d; };
+        auto fetch = [&](const RowEnt& r) -> Pre {
+            Pre o{-1, 0.0f};
+            const int j = w + NGATHER * lane;
+            if (r.n > 0 && j < r.n) {
+                o.idx = __ldg(p.indices + r.lo + j);
+                o.d = __ldg(p.data + r.lo + j);
+            }
+            return o;
+        };
+        RowEnt cur = ent_at(0), nxt = ent_at(1);
+        Pre pc = fetch(cur);
         for (int k = 0; k < nslots; ++k) {
-            const RowEnt e = nxt;
-            nxt = ent_at(k + 1);
+            const RowEnt e = cur;
+            const Pre pe = pc;
+            cur = nxt;
+            nxt = ent_at(k + 2);
+            pc = fetch(cur);
             if (e.n <= 0) continue;
             const int n = e.n, n16 = (n + 15) & ~15;
             const float S = exp2f((float)e.sexp);
-            // this warp's entries j = w, w + NGATHER, ...: lane l holds entry w + NGATHER l
-            int my_idx = -1;
+            const int my_idx = pe.idx;
             float my_s = 0.0f;
-            {
-                const int j = w + NGATHER * lane;
-                if (j < n) {
-                    my_idx = __ldg(p.indices + e.lo + j);
-                    float d = __ldg(p.data + e.lo + j);
-                    if (p.bias) d = __fsub_rn(d, __ldg(p.Yraw + (int64_t)my_idx * p.ldraw));  // wmf_model.py:343
-                    my_s = S * sqrtf(d);
-                }
+            if (my_idx >= 0) {
+                float d = pe.d;
+                if (p.bias) d = __fsub_rn(d, __ldg(p.Yraw + (int64_t)my_idx * p.ldraw));  // wmf_model.py:343
+                my_s = S * sqrtf(d);
             }
             const int cnt = (n16 - w + NGATHER - 1) / NGATHER;     // entries (padding rows included) this warp writes
-            uint32_t sbase[2];                      // stage of this lane's chunk, per pass
-#pragma unroll
-            for (int ps = 0; ps < 2; ++ps) {
-                const uint32_t gs = gsi + (uint32_t)(ps * 2 + csel);
-                sbase[ps] = smem_base + OFF_STAGES + (gs % NST) * PAIR_BYTES;
-            }
             for (int c = 0; c < KCH; ++c) {
                 const uint32_t gs = gsi + (uint32_t)c;
                 mbar_wait(bar_empty(gs % NST), ((gs / NST) & 1u) ^ 1u);
             }
-            for (int e0 = 0; e0 < cnt; e0 += 4) {
-                float4 v[4][2];
-                int idxs[4];
-                float ss[4];
+            for (int ps = 0; ps < PASSES; ++ps) {
+                const uint32_t sb = smem_base + OFF_STAGES + ((gsi + (uint32_t)(ps * 2 + csel)) % NST) * PAIR_BYTES;
+                const float* ybase = p.Y + ps * 128 + lane * 4;
+                auto load4 = [&](int e0, float4 (&v)[4]) {   // e0, cnt are warp-uniform
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    idxs[b] = __shfl_sync(0xffffffffu, my_idx, (e0 + b) & 31);
-                    ss[b] = __shfl_sync(0xffffffffu, my_s, (e0 + b) & 31);
-                    if (e0 + b >= cnt) idxs[b] = -2;   // past this warp's share: nothing to write
-#pragma unroll
-                    for (int ps = 0; ps < 2; ++ps) {
-                        v[b][ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (idxs[b] >= 0 && ps < PASSES)
-                            v[b][ps] = __ldg(reinterpret_cast<const float4*>(p.Y + (int64_t)idxs[b] * FP + ps * 128) + lane);
+                    for (int b = 0; b < 4; ++b) {
+                        const int idx = __shfl_sync(0xffffffffu, my_idx, (e0 + b) & 31);
+                        v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e0 + b < cnt && idx >= 0) v[b] = __ldg(reinterpret_cast<const float4*>(ybase + (int64_t)idx * FP));
                     }
-                }
+                };
+                auto store4 = [&](int e0, const float4 (&v)[4]) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (idxs[b] == -2) continue;
-                    const uint32_t j = (uint32_t)(w + NGATHER * (e0 + b));
-                    const uint32_t roff = (j >> 3) * 1024u + (j & 7u) * 128u + (((q ^ (j & 7u))) << 4) + half8;
-#pragma unroll
-                    for (int ps = 0; ps < 2; ++ps) {
-                        if (ps >= PASSES) break;
-                        const float z0 = ss[b] * v[b][ps].x, z1 = ss[b] * v[b][ps].y, z2 = ss[b] * v[b][ps].z, z3 = ss[b] * v[b][ps].w;
+                    for (int b = 0; b < 4; ++b) {
+                        const float ss = __shfl_sync(0xffffffffu, my_s, (e0 + b) & 31);
+                        if (e0 + b >= cnt) continue;   // past this warp's share: nothing to write
+                        const uint32_t j = (uint32_t)(w + NGATHER * (e0 + b));
+                        const uint32_t roff = (j >> 3) * 1024u + (j & 7u) * 128u + (((q ^ (j & 7u))) << 4) + half8;
+                        const float z0 = ss * v[b].x, z1 = ss * v[b].y, z2 = ss * v[b].z, z3 = ss * v[b].w;
                         const __half2 h01 = __floats2half2_rn(z0, z1), h23 = __floats2half2_rn(z2, z3);
                         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                         const __half2 l01 = __floats2half2_rn(z0 - f01.x, z1 - f01.y), l23 = __floats2half2_rn(z2 - f23.x, z3 - f23.y);
-                        sts2u(sbase[ps] + roff, h2_bits(h01), h2_bits(h23));
-                        sts2u(sbase[ps] + TILE_BYTES + roff, h2_bits(l01), h2_bits(l23));
+                        sts2u(sb + roff, h2_bits(h01), h2_bits(h23));
+                        sts2u(sb + TILE_BYTES + roff, h2_bits(l01), h2_bits(l23));
                     }
+                };
+                float4 va[4], vb[4];
+                load4(0, va);
+                for (int e0 = 0; e0 < cnt; e0 += 8) {
+                    if (e0 + 4 < cnt) load4(e0 + 4, vb);
+                    store4(e0, va);
+                    if (e0 + 8 < cnt) load4(e0 + 8, va);
+                    if (e0 + 4 < cnt) store4(e0 + 4, vb);
                 }
             }
             fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -254,6 +264,10 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
         const uint32_t d_tmem = tmem_base + (uint32_t)(g * ACC_COLS);
         const uint64_t descH = umma_desc_panel(tileH), descL = umma_desc_panel(tileL);
         uint32_t row_n = 0, panel_n = 0;
+#ifdef WMF_TC_PROFILE_BUILD
+        const bool prof = p.prof != nullptr && blockIdx.x == 0 && g == 0 && t == 0;
+        long long pf_t0 = prof ? clock64() : 0, pf_acc = 0, pf_cg = 0, pf_xp = 0, pf_rows = 0, pf_prod = 0, pf_n = 0, pf_a = 0, pf_b = 0;
+#endif
         RowEnt nxt = ent_at(0);
         for (int k = 0; k < nslots; ++k) {
             const RowEnt e = nxt;
@@ -273,7 +287,13 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                 sq = sqrtf(d);
                 bt = __fdiv_rn(__fadd_rn(d, 1.0f), sq);
             }
+#ifdef WMF_TC_PROFILE_BUILD
+            if (prof) pf_a = clock64();
+#endif
             mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);
+#ifdef WMF_TC_PROFILE_BUILD
+            if (prof) { pf_b = clock64(); pf_acc += pf_b - pf_a; ++pf_rows; pf_n += n; }
+#endif
             tc_fence_after();
             // a warp whose 32 lanes lie beyond the padded system (n <= 32: three of the four) owns no matrix row: it
             // only keeps the group's barriers (and, if it is warp g, the pivot factor) and skips the per-row work
@@ -286,6 +306,9 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                 float xc = 0.0f;
                 int products = -1;
                 if (active) products = cg_solve(t_row, t, n16, bt, inv_s2, bfin, Dblk, qw, (n16 + 31) >> 5, CG_BAR0 + g, ((n16 + 31) >> 5) * 32, p.cg_maxit, xc);
+#ifdef WMF_TC_PROFILE_BUILD
+                if (prof) pf_prod += products;
+#endif
                 const uint32_t flag = Dblk + 128u + (rn & 4u);   // alternates between this group's consecutive rows
                 if (t == 0) sts1(flag, products >= 0 ? 1.0f : 0.0f);
                 tc_fence_before();
@@ -451,34 +474,69 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pairs + (uint32_t)t * 8u), "r"(__float_as_uint(coef)),
                          "r"((uint32_t)my_idx) : "memory");
             named_bar(bar_id, GROUP);
-            // ---- x'[m] = sum_j coef_j y~_j[m]: thread t sums feature t (and t + 128), entries in ascending order ----
+#ifdef WMF_TC_PROFILE_BUILD
+            if (prof) { pf_a = clock64(); pf_cg += pf_a - pf_b; }
+#endif
+            // ---- x'[m] = sum_j coef_j y~_j[m]. Warp qw takes the entries j = qw, qw + 4, ... (ascending) and lane l the
+            // features 4 l .. 4 l + 3 of a 128-feature pass: one coalesced 512-byte read per factor row (the rows the gather
+            // warps have just pulled through L2), the next four rows in flight while four are added; the four warps'
+            // partial sums meet in shared memory (the panel tiles of the factorisation are free here) and thread t adds
+            // them in warp order. A function of the row alone, like everything else. ----
             {
-                float acc0 = 0.0f, acc1 = 0.0f;
-                const int n4 = (n + 3) & ~3;
-                const float* yb = p.Y + t;
-                for (int j = 0; j < n4; j += 4) {
-                    uint32_t c[8];
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "r"(pairs + (uint32_t)j * 8u));
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]) : "r"(pairs + (uint32_t)j * 8u + 16u));
-                    float y0[4], y1[4];
+                const uint32_t xpart = tileH;   // 4 warps x 256 floats
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float* yb = p.Y + ps * 128 + lane * 4;
+                    auto load4 = [&](int j, float (&c)[4], float4 (&y)[4]) {   // j, n are warp-uniform
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const float* src = yb + (int64_t)c[2 * b + 1] * FP;
-                        y0[b] = __ldg(src);
-                        y1[b] = PASSES > 1 ? __ldg(src + 128) : 0.0f;
-                    }
+                        for (int b = 0; b < 4; ++b) {
+                            c[b] = 0.0f;
+                            y[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (j + 4 * b < n) {
+                                uint32_t cw, ci;
+                                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(cw), "=r"(ci) : "r"(pairs + (uint32_t)(j + 4 * b) * 8u));
+                                c[b] = __uint_as_float(cw);
+                                y[b] = __ldg(reinterpret_cast<const float4*>(yb + (int64_t)ci * FP));
+                            }
+                        }
+                    };
+                    auto add4 = [&](const float (&c)[4], const float4 (&y)[4]) {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        acc0 = fmaf(__uint_as_float(c[2 * b]), y0[b], acc0);
-                        acc1 = fmaf(__uint_as_float(c[2 * b]), y1[b], acc1);
+                        for (int b = 0; b < 4; ++b) {
+                            acc.x = fmaf(c[b], y[b].x, acc.x); acc.y = fmaf(c[b], y[b].y, acc.y);
+                            acc.z = fmaf(c[b], y[b].z, acc.z); acc.w = fmaf(c[b], y[b].w, acc.w);
+                        }
+                    };
+                    float ca[4], cb[4];
+                    float4 ya[4], yv[4];
+                    load4(qw, ca, ya);
+                    for (int j = qw; j < n; j += 32) {
+                        if (j + 16 < n) load4(j + 16, cb, yv);
+                        add4(ca, ya);
+                        if (j + 32 < n) load4(j + 32, ca, ya);
+                        if (j + 16 < n) add4(cb, yv);
                     }
+                    sts4(xpart + (uint32_t)((qw * 256 + ps * 128 + lane * 4) * 4), acc.x, acc.y, acc.z, acc.w);
                 }
+                named_bar(bar_id, GROUP);
                 float* xout = p.X + (int64_t)e.row * p.ldx;
-                xout[t] = acc0;
-                if (PASSES > 1) xout[128 + t] = acc1;
+                {
+                    const uint32_t a = xpart + (uint32_t)t * 4u;
+                    xout[t] = ((lds1(a) + lds1(a + 1024)) + lds1(a + 2048)) + lds1(a + 3072);
+                    if (PASSES > 1) xout[128 + t] = ((lds1(a + 512) + lds1(a + 1536)) + lds1(a + 2560)) + lds1(a + 3584);
+                }
             }
             named_bar(bar_id, GROUP);  // pairs / Nst / bfin are rewritten by the next row
+#ifdef WMF_TC_PROFILE_BUILD
+            if (prof) pf_xp += clock64() - pf_a;
+#endif
         }
+#ifdef WMF_TC_PROFILE_BUILD
+        if (prof) {
+            p.prof[40] = clock64() - pf_t0; p.prof[41] = pf_acc; p.prof[42] = pf_cg; p.prof[43] = pf_xp; p.prof[44] = pf_rows;
+            p.prof[45] = pf_prod; p.prof[46] = pf_n;
+        }
+#endif
     }
     // =============================== TEARDOWN ===============================
     tc_fence_before();

@@ -65,22 +65,36 @@ static_assert(STAGES == 4 || STAGES == 6, "operand stages");
 constexpr int F = 128;               // factor width handled by this kernel
 constexpr int SUB = 32;              // stored entries per sub-chunk (one pipeline stage)
 constexpr int NSTAGE = STAGES;       // operand stages (two sub-chunks share one 128-byte-swizzled tile pair)
-constexpr int NTEAM = 2;             // gather teams
+constexpr int NTEAM = 2;             // gather teams (a TMA producer warp + four transform warps each)
 constexpr int NSTG = STAGING;        // raw staging buffers per team (TMA gathers in flight)
 constexpr int TILE_BYTES = F * 128;  // 128 rows (features) x 64 fp16 (K) = 16 KB, holds two sub-chunks
 constexpr int PAIR_BYTES = 2 * TILE_BYTES;   // [zh ; zl]
 constexpr int STG_BYTES = SUB * F * 4;       // 32 gathered factor rows, row-major fp32, 16 KB
-constexpr int META_BYTES = SUB * 8 + 16;     // per staging buffer: S*sqrt(d) [32], d+1 [32], then the sub-chunk's descriptor
+constexpr int META_BYTES = SUB * 8 + 16;     // per staging buffer: S*sqrt(d) [32], (unused) [32], then the sub-chunk's descriptor
 constexpr int NB = 8;                // Gauss-Jordan step width
-constexpr int NGROUP = 4;            // solver groups = TMEM accumulators
+// A operands of the Gram MMAs from tensor memory (WMF_TC_A_TMEM, default): the transform thread of feature m holds
+// exactly row m of the K-major A tiles in registers, so it stores them into TMEM lane m (tcgen05.st) and only the
+// B operands are read from shared memory: 12 KB instead of 24 KB per 16 entries on the resource that bounds this
+// kernel. The four operand stages take 128 TMEM columns, which leaves three accumulators (systems in flight).
+#ifndef WMF_TC_A_TMEM
+#define WMF_TC_A_TMEM 1
+#endif
+constexpr bool A_TMEM = WMF_TC_A_TMEM != 0;
+constexpr int NGROUP = A_TMEM ? 3 : 4;   // solver groups = TMEM accumulators
+constexpr int OPND_COL0 = NGROUP * 128;  // first TMEM column of the A-operand stages (32 columns each: hi 16 | lo 16)
 constexpr int GROUP = 128;
 constexpr int TEAM = 128;
-constexpr int SOLVER_WARP0 = 0, GATHER_WARP0 = NGROUP * 4, MMA_WARP = GATHER_WARP0 + NTEAM * 4;  // high warp ids issue first
+#ifndef WMF_TC_SOLVERS_FIRST
+#define WMF_TC_SOLVERS_FIRST 1
+#endif
+// warp ids of the roles (solver warps start at a multiple of 4: warp id mod 4 is the TMEM lane quarter)
+constexpr int GATHER_WARP0 = WMF_TC_SOLVERS_FIRST ? NGROUP * 4 : 0, SOLVER_WARP0 = WMF_TC_SOLVERS_FIRST ? 0 : NTEAM * 4;
+constexpr int MMA_WARP = (NGROUP + NTEAM) * 4;
 constexpr int PRODUCER_WARP0 = MMA_WARP + 1;               // one TMA producer warp per gather team
 constexpr int THREADS = (PRODUCER_WARP0 + NTEAM) * 32;     // 864
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int CG_BAR0 = 1 + NGROUP;  // named barriers 1 .. NGROUP: a whole solver group; CG_BAR0 + g: its warps that hold rows
-static_assert(NGROUP * F <= 512, "TMEM columns");
+static_assert(NGROUP * F + (A_TMEM ? NSTAGE * 32 : 0) <= 512, "TMEM columns");
 
 // per-group shared memory
 constexpr int PANEL_TILE_BYTES = F * NB * 4;          // 4 KB: 128 rows x 8 fp32, K-major, no swizzle
@@ -370,7 +384,7 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
 
     if (warp >= PRODUCER_WARP0) {
         // =============================== GATHER: TMA PRODUCER ===============================
-        // One warp per team. It walks the rows of this CTA, takes the sub-chunks c with (c + row_n + T) even and, for
+        // One warp per team. It walks the rows of this CTA, takes the sub-chunks c with (c + row_n) mod NTEAM == T and, for
         // each, has the 32 gathered factor rows copied into one of the team's raw staging buffers by the TMA unit:
         // eight cp.async.bulk.tensor ... tile::gather4 (four rows of 512 B each, lanes 0-7 issue one apiece) that
         // complete on the buffer's mbarrier. Beside the rows it leaves the per-entry scales S*sqrt(d), d+1 and a
@@ -386,7 +400,7 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
         float cu_S = 1.0f;    // FP16 scale of the row
         RowEnt w0 = ent_at(0), w1 = ent_at(1);  // prefetched table entries k+1, k+2
         auto advance = [&](bool first) {  // to the team's next sub-chunk
-            if (!first) cu_c += 2;
+            if (!first) cu_c += NTEAM;
             while (cu_k < nslots && cu_c >= cu_nsub) {
                 bool found = false;
                 while (!found) {  // next non-empty row
@@ -403,14 +417,14 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
                     }
                 }
                 if (!found) break;
-                cu_c = (team + cu_row_n) & 1;
+                cu_c = ((team - cu_row_n) % NTEAM + NTEAM) % NTEAM;   // the team takes the sub-chunks c with (c + row_n) % NTEAM == team
             }
         };
         struct Raw { int idx; float d; float s; int gi; int row_n; int last; };
         auto load_raw = [&]() {  // lane l: entry l of the cursor's sub-chunk
             Raw rw{-1, 0.f, cu_S, -1, 0, 0};
             if (cu_k < nslots) {
-                rw.gi = cu_gi0 + cu_c; rw.row_n = cu_row_n; rw.last = cu_c + 2 >= cu_nsub ? 1 : 0;
+                rw.gi = cu_gi0 + cu_c; rw.row_n = cu_row_n; rw.last = cu_c + NTEAM >= cu_nsub ? 1 : 0;
                 const int off = cu_c * SUB + lane;
                 if (off < cu_n) {
                     rw.d = __ldg(p.data + cu_lo + off);      // loads only (see above)
@@ -435,14 +449,10 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
             }
             if (p.bias && rw.idx >= 0) rw.d = __fsub_rn(rw.d, __ldg(p.Yraw + (int64_t)rw.idx * p.ldraw));  // wmf_model.py:343
             {
-                float sq = 0.f, dp1 = 0.f;
-                if (rw.idx >= 0) {  // rows with a negative weight never get here (fix-up list, tc_prep_rows_kernel)
-                    sq = rw.s * sqrtf(rw.d);
-                    dp1 = __fadd_rn(rw.d, 1.0f);
-                }
+                float sq = 0.f;
+                if (rw.idx >= 0) sq = rw.s * sqrtf(rw.d);  // rows with a negative weight never get here (fix-up list, tc_prep_rows_kernel)
                 sts1(mt + lane * 4, sq);
-                sts1(mt + SUB * 4 + lane * 4, dp1);
-                if (lane == 0) sts4u(mt + SUB * 8, (uint32_t)rw.gi, (uint32_t)rw.row_n, (uint32_t)rw.last, 0u);
+                if (lane == 0) sts4u(mt + SUB * 8, (uint32_t)rw.gi, (uint32_t)rw.row_n, (uint32_t)rw.last, __float_as_uint(1.0f / (rw.s * rw.s)));
             }
             const int vi = rw.idx >= 0 ? rw.idx : oob_row;
             const int i0 = __shfl_sync(0xffffffffu, vi, (4 * lane) & 31), i1 = __shfl_sync(0xffffffffu, vi, (4 * lane + 1) & 31);
@@ -460,7 +470,7 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
             }
             ++jp;
         }
-    } else if (warp >= GATHER_WARP0 && warp < MMA_WARP) {
+    } else if (warp >= GATHER_WARP0 && warp < GATHER_WARP0 + NTEAM * 4) {
         // =============================== GATHER: TRANSFORM ===============================
         // Two teams of 128 threads; thread m owns feature m. A team takes the staging buffers its producer warp fills
         // in order: thread m reads column m of the 32 raw rows, scales, splits to FP16 hi/lo and stores the K-major
@@ -480,44 +490,49 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
             const uint32_t stg = smem_base + OFF_STG + (team * NSTG + sb) * STG_BYTES + m * 4;
             const uint32_t mt = smem_base + OFF_META + (team * NSTG + sb) * META_BYTES;
             int d_gi, d_row_n, d_last;
+            float d_inv_s2;
             {
                 uint32_t a, b, c, d;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(mt + SUB * 8));
-                d_gi = (int)a; d_row_n = (int)b; d_last = (int)c;
+                d_gi = (int)a; d_row_n = (int)b; d_last = (int)c; d_inv_s2 = __uint_as_float(d);
             }
             if (d_gi < 0) break;
             const int s = d_gi % NSTAGE;
             mbar_wait(bar_empty(s), (((uint32_t)d_gi / NSTAGE) & 1u) ^ 1u);
             if (prof) { t2 = clock64(); t_empty += t2 - tt; tt = t2; }
+            if (A_TMEM) tc_fence_after();   // the MMAs that read this stage's TMEM operands have completed
             const uint32_t tile_h = smem_base + OFF_STAGES + (s >> 1) * PAIR_BYTES + m * 128;
+            const uint32_t opnd = tmem_base + ((uint32_t)((m >> 5) * 32) << 16) + (uint32_t)(OPND_COL0 + s * 32);
             const int half = s & 1;
-            float part = 0.f;
+            // rhs partial: sum (d + 1) v = sum v + (1 / S^2) sum z sq  with z = sq v, sq = S sqrt(d) (one scale per entry
+            // to read instead of two: this kernel is bound by shared-memory wavefronts)
+            float part1 = 0.f, partd = 0.f;
             // The shared-memory accessors are volatile asm (program order is issue order), so the loads of chunk c+1
             // are written ahead of the arithmetic and stores of chunk c: one LDS latency is exposed per sub-chunk
             // instead of one per 8 entries.
-            float vn[8], sqn[8], dpn[8];
+            float vn[8], sqn[8];
             auto load_chunk = [&](int c) {
                 const float4 sa = lds4(mt + c * 32), sb4 = lds4(mt + c * 32 + 16);
-                const float4 da = lds4(mt + SUB * 4 + c * 32), db = lds4(mt + SUB * 4 + c * 32 + 16);
                 sqn[0] = sa.x; sqn[1] = sa.y; sqn[2] = sa.z; sqn[3] = sa.w; sqn[4] = sb4.x; sqn[5] = sb4.y; sqn[6] = sb4.z; sqn[7] = sb4.w;
-                dpn[0] = da.x; dpn[1] = da.y; dpn[2] = da.z; dpn[3] = da.w; dpn[4] = db.x; dpn[5] = db.y; dpn[6] = db.z; dpn[7] = db.w;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) vn[e] = lds1(stg + (c * 8 + e) * (F * 4));
             };
             load_chunk(0);
 #pragma unroll
             for (int c = 0; c < SUB / 8; ++c) {   // one 16-byte chunk = 8 entries of this feature
-                float v[8], sq[8], dp[8];
+                float v[8], sq[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { v[e] = vn[e]; sq[e] = sqn[e]; dp[e] = dpn[e]; }
+                for (int e = 0; e < 8; ++e) { v[e] = vn[e]; sq[e] = sqn[e]; }
                 if (c + 1 < SUB / 8) load_chunk(c + 1);
                 uint32_t hh[4], ll[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float v0 = v[2 * e], v1 = v[2 * e + 1];
                     const float z0 = sq[2 * e] * v0, z1 = sq[2 * e + 1] * v1;
-                    part = fmaf(dp[2 * e], v0, part);
-                    part = fmaf(dp[2 * e + 1], v1, part);
+                    part1 += v0;
+                    partd = fmaf(z0, sq[2 * e], partd);
+                    part1 += v1;
+                    partd = fmaf(z1, sq[2 * e + 1], partd);
                     const __half2 h = __floats2half2_rn(z0, z1);
                     const float2 hf = __half22float2(h);
                     const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
@@ -527,7 +542,13 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
                 const uint32_t sw = (uint32_t)(((half * 4 + c) ^ (m & 7)) << 4);  // 128B swizzle: chunk index XOR (row mod 8)
                 sts4u(tile_h + sw, hh[0], hh[1], hh[2], hh[3]);
                 sts4u(tile_h + TILE_BYTES + sw, ll[0], ll[1], ll[2], ll[3]);
+                if (A_TMEM) {   // row m of the A tiles: K-step c / 2, words 4 (c & 1) .. of its 8 columns
+                    tmem_st4(opnd + (uint32_t)(c * 4), hh[0], hh[1], hh[2], hh[3]);
+                    tmem_st4(opnd + 16u + (uint32_t)(c * 4), ll[0], ll[1], ll[2], ll[3]);
+                }
             }
+            const float part = fmaf(partd, d_inv_s2, part1);
+            if (A_TMEM) { tmem_wait_st(); tc_fence_before(); }
             bacc += (double)part;
             fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full(s));
@@ -584,13 +605,25 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
                     }
                     if (elect_one()) {
                         // 16 fp16 = 32 B along K inside the 128-B swizzle row per K-step; a sub-chunk is one or two of them
-                        umma_f16(d_tmem, dh, dh, idesc_gram, accumulate);  // zh zh^T
-                        umma_f16(d_tmem, dh, dl, idesc_gram, 1u);          // zh zl^T
-                        umma_f16(d_tmem, dl, dh, idesc_gram, 1u);          // zl zh^T
-                        if (kc > 16) {
-                            umma_f16(d_tmem, dh + 2, dh + 2, idesc_gram, 1u);
-                            umma_f16(d_tmem, dh + 2, dl + 2, idesc_gram, 1u);
-                            umma_f16(d_tmem, dl + 2, dh + 2, idesc_gram, 1u);
+                        if (A_TMEM) {
+                            const uint32_t ah = tmem_base + (uint32_t)(OPND_COL0 + s * 32), al = ah + 16u;
+                            umma_f16_ts(d_tmem, ah, dh, idesc_gram, accumulate);  // zh zh^T
+                            umma_f16_ts(d_tmem, ah, dl, idesc_gram, 1u);          // zh zl^T
+                            umma_f16_ts(d_tmem, al, dh, idesc_gram, 1u);          // zl zh^T
+                            if (kc > 16) {
+                                umma_f16_ts(d_tmem, ah + 8u, dh + 2, idesc_gram, 1u);
+                                umma_f16_ts(d_tmem, ah + 8u, dl + 2, idesc_gram, 1u);
+                                umma_f16_ts(d_tmem, al + 8u, dh + 2, idesc_gram, 1u);
+                            }
+                        } else {
+                            umma_f16(d_tmem, dh, dh, idesc_gram, accumulate);  // zh zh^T
+                            umma_f16(d_tmem, dh, dl, idesc_gram, 1u);          // zh zl^T
+                            umma_f16(d_tmem, dl, dh, idesc_gram, 1u);          // zl zh^T
+                            if (kc > 16) {
+                                umma_f16(d_tmem, dh + 2, dh + 2, idesc_gram, 1u);
+                                umma_f16(d_tmem, dh + 2, dl + 2, idesc_gram, 1u);
+                                umma_f16(d_tmem, dl + 2, dh + 2, idesc_gram, 1u);
+                            }
                         }
                         tc_commit(bar_empty(s));
                     }
@@ -623,7 +656,7 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
         // the group's barriers (and, if it is warp g, the pivot factor) and skips the per-row work
         const bool active = q * 32 < f16;
         const int nact = (f16 + 31) >> 5;   // warps of the group that hold matrix rows
-        uint32_t row_n = 0, panel_n = 0, cnt_b0 = 0, cnt_b1 = 0;
+        uint32_t row_n = 0, panel_n = 0, b_phase = 0;
         const bool prof = PROF && blockIdx.x == 0 && g == 0 && t == 0;
         long long t_accfull = 0, t_fact = 0, t_back = 0, t_start = prof ? clock64() : 0, tt = 0;
         long long ph_wait = 0, ph_ld = 0, ph_own = 0, ph_p = 0, ph_issue = 0, t3 = 0, t4 = 0, my_rows = 0, cg_rows = 0, cg_products = 0;
@@ -638,15 +671,21 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
             float* xout = p.X + (int64_t)e.row * p.ldx;
             const float S = exp2f((float)e.sexp), inv_s = exp2f((float)-e.sexp), inv_s2 = inv_s * inv_s;  // exact powers of two
             if (prof) tt = clock64();
-            // rhs partials: the team that owns sub-chunk 0 always delivers, the other one if the row has two or more
-            const int t0 = rn & 1;
-            float bt;
+            // rhs partials: one per residue class c mod NTEAM of the row's sub-chunks (class k is the work of team
+            // (k + row_n) mod NTEAM), added in class order: a function of the row alone
+            float bt = 0.0f;
             {
-                float bA = 0.0f, bB = 0.0f;  // team 0, team 1
-                const bool both = e.n > SUB;
-                if (t0 == 0 || both) { mbar_wait(bar_b_full(g, 0), cnt_b0 & 1u); ++cnt_b0; bA = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 0) * F + t) * 4); }
-                if (t0 == 1 || both) { mbar_wait(bar_b_full(g, 1), cnt_b1 & 1u); ++cnt_b1; bB = lds1(smem_base + OFF_BVEC + ((g * NTEAM + 1) * F + t) * 4); }
-                bt = bA + bB;
+                const int nsub_row = (e.n + SUB - 1) / SUB;
+#pragma unroll
+                for (int cls = 0; cls < NTEAM; ++cls) {
+                    if (cls < nsub_row) {
+                        const int tm = (cls + (int)(rn % NTEAM)) % NTEAM;
+                        mbar_wait(bar_b_full(g, tm), (b_phase >> tm) & 1u);
+                        b_phase ^= 1u << tm;
+                        const float bp = lds1(smem_base + OFF_BVEC + ((g * NTEAM + tm) * F + t) * 4);
+                        bt = cls == 0 ? bp : bt + bp;
+                    }
+                }
             }
             mbar_arrive(bar_b_empty(g));
             mbar_wait(bar_acc_full(g), (rn / NGROUP) & 1u);

@@ -17,7 +17,7 @@ def run(csr, Yd, name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); X = engine.half_step(csr, Yd, G, algo=_lib.ALGO_TCGEN05); e1.record(); torch.cuda.synchronize()
     ws = engine.workspace(0, dev)
-    prof = ws[256:256 + 512].view(torch.int64).cpu().numpy()
+    prof = ws[256:256 + 640].view(torch.int64).cpu().numpy()
     flags = ws[0:8].view(torch.int32).cpu().numpy()
     ms = e0.elapsed_time(e1)
     print(f"{name}: {ms:.2f} ms  flags={flags}")
@@ -29,6 +29,9 @@ def run(csr, Yd, name):
     print("  solver phases (thread 0 of group 0): wait_mma", f(prof[24]), "tmem_ld", f(prof[25]), "own_factor(4 of 16 panels)", f(prof[26]),
           "barA", f(prof[27]), "P", f(prof[28]), "split+sts+fence", f(prof[29]), "barB", f(prof[30]), "mma_issue", f(prof[31]))
     print("  cg: rows solved", prof[32], "of", prof[22], " products", prof[33])
+    if prof[44] > 0:
+        print("  dual kernel, group 0 of CTA 0: total", f(prof[40]), "wait acc_full", f(prof[41]), "cg", f(prof[42]), "x'", f(prof[43]),
+              "rows", prof[44], "products", prof[45], "entries", prof[46])
     return X
 U = run(Cd, Y, "user half-step")
 V = run(CT, U, "item half-step")
