@@ -419,9 +419,12 @@ def run_ours(args):
     peak = float(peaks["hbm_gbs"])
     achieved = (bytes_user + bytes_item) / ((t_user + t_item) * 1e-3) / 1e9
     flops = (C.nnz + CT.nnz) * (2.0 * f * f + 2 * f) + (C.shape[0] + CT.shape[0]) * (f ** 3 / 3.0 + 2.0 * f * f)
-    # what the tensor pipe executes at f = 128: 3 FP16 passes of the Gram (n f^2 MACs each) and 3 TF32 passes of the
-    # rank-8 Gauss-Jordan updates (~f^3 / 2 MACs per row); reported against the sustained bf16 peak
-    tensor_flops = 3 * 2.0 * f * f * (C.nnz + CT.nnz) + 3 * 1.0 * f ** 3 * (C.shape[0] + CT.shape[0])
+    # what the tensor pipe executes: 3 FP16 passes of the Gram (n f^2 MACs each, every row counted in its primal form;
+    # the solves are conjugate gradients on the CUDA cores), reported against the sustained bf16 peak; under
+    # --algo tcgen05_direct the 3 TF32 passes of the rank-8 Gauss-Jordan updates (~f^3 / 2 MACs per row) come on top
+    tensor_flops = 3 * 2.0 * f * f * (C.nnz + CT.nnz)
+    if args.algo == "tcgen05_direct":
+        tensor_flops += 3 * 1.0 * f ** 3 * (C.shape[0] + CT.shape[0])
     launches_per_epoch = loop.launches_per_epoch
 
     # ---- eval_prec alone (reported separately): MSE over the stored entries of the count matrix
@@ -499,7 +502,10 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload),
             "run": {"algo": args.algo, "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
-                    "launch": launch_mode, "exchange": loop.exchange_mode},
+                    "launch": launch_mode, "exchange": loop.exchange_mode,
+                    "solver": ("block Gauss-Jordan in tensor memory" if args.algo == "tcgen05_direct" else
+                               "conjugate gradients on the system matrix in tensor memory (relative residual 1e-6; "
+                               "rows that do not converge in 64 products are factorised in tensor memory)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note + "; algorithmic bytes = %d" % (bytes_user + bytes_item),
                          "peak_kind": peak_kind, "kernel": "als half-step stage (whiten, dual + primal tcgen05 kernels, unwhiten; 2 per epoch)",
@@ -508,8 +514,10 @@ def run_ours(args):
                          "tensor": {"executed_tflops": tensor_flops / ((t_user + t_item) * 1e-3) / 1e12,
                                     "peak": float(peaks["bf16_tflops_sustained"]),
                                     "frac": tensor_flops / ((t_user + t_item) * 1e-3) / 1e12 / float(peaks["bf16_tflops_sustained"]),
-                                    "what": "3 FP16 passes of the Gram + 3 TF32 passes of the Gauss-Jordan updates vs the "
-                                            "sustained bf16 peak (TF32 runs at half that rate)"}},
+                                    "what": "3 FP16 passes of the Gram (every row counted in its primal form) vs the sustained bf16 "
+                                            "peak; the solves are conjugate gradients on the CUDA cores"
+                                            + (" (+ 3 TF32 passes of the Gauss-Jordan updates: --algo tcgen05_direct)"
+                                               if args.algo == "tcgen05_direct" else "")}},
             "eval_prec": {"ms": eval_ms, "gbs": eval_bytes / (eval_ms * 1e-3) / 1e9, "frac_of_hbm_peak": eval_bytes / (eval_ms * 1e-3) / 1e9 / peak,
                           "what": f"sddmm_loss over the {C.nnz} stored entries of this rank's rows (base_model.py:150-179), "
                                   f"algorithmic {eval_bytes} bytes"},

@@ -50,6 +50,14 @@ int wmf_als_half_step_status(const void* ws, int* flags_host, int* fixup_rows_ho
     return WMF_OK;
 }
 
+int wmf_als_half_step_fallback_rows(const void* ws, int* rows_host, void* stream) {
+    WMF_REQUIRE(ws != nullptr && rows_host != nullptr, "wmf_als_half_step_fallback_rows: null pointer");
+    WMF_CUDA(cudaMemcpyAsync(rows_host, reinterpret_cast<const int*>(ws) + 12, sizeof(int), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    WMF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return WMF_OK;
+}
+
 int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float* data, int64_t rows, int64_t cols,
                       const int32_t* row_order, int64_t order_len, const float* Y, int64_t ldy, int f,
                       const float* G, int bias,

@@ -318,6 +318,7 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
                     mbar_arrive(bar_acc_empty(g));   // the Gram of this group's next row may start
                     coef = t < n ? xc * sq : 0.0f;
                 } else {
+                    if (t == 0) atomicAdd(flags + 11, 1);   // header word 12: rows the factorisation had to take
                     tc_fence_after();
                 }
             }

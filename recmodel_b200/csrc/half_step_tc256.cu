@@ -361,6 +361,7 @@ als_half_step_tc256_kernel(HalfStepParams p, const int4* __restrict__ rowtab, co
                     xout[t] = t < f8 ? xc : 0.0f;
                     continue;
                 }
+                if (t == 0) atomicAdd(flags + 11, 1);   // header word 12: rows the factorisation had to take
             }
 #pragma unroll 1
             for (int c0 = 0; c0 < f8; c0 += NB) {

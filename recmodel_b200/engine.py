@@ -426,6 +426,23 @@ def half_step_status(ws=None):
     return flags.value, fixed.value
 
 
+def half_step_fallback_rows(ws=None):
+    """Rows of the last tcgen05 half-step that used ``ws`` whose conjugate gradients did not converge within their
+    product budget and were factorised in tensor memory instead (synchronises the stream)."""
+    import ctypes
+    lib = _lib.load()
+    if ws is None:
+        ref = getattr(half_step, "last_ws", None)
+        ws = ref() if ref is not None else None
+    if ws is None:
+        return 0
+    rows = ctypes.c_int(0)
+    with _on(ws.device):
+        _lib.check(lib.wmf_als_half_step_fallback_rows(_ptr(ws), ctypes.addressof(rows), _stream(ws.device)),
+                   "wmf_als_half_step_fallback_rows")
+    return rows.value
+
+
 @_device_of(1)
 def sddmm_loss(csr, U, V, bias=False):
     """Device tensor [sum sq err, sum abs err, count] (float64) over the non-zero stored entries

@@ -263,6 +263,42 @@ def test_half_step_indefinite_falls_back_to_lu(cuda_device, algo_name, algo):
         assert fixed == int((np.diff(C.indptr) > 0).sum()) and (flags & 2) == 0
 
 
+@pytest.mark.parametrize("f", [32, 128, 200])
+def test_half_step_cg_falls_back_to_factorisation(cuda_device, f):
+    """Weights in the thousands (linear preprocessing of large counts) put the whitened systems at condition numbers
+    the conjugate gradients do not resolve within their product budget: those rows are factorised in tensor memory
+    instead (the block Gauss-Jordan that WMF_ALGO_TCGEN05_DIRECT applies to every row), from the untouched matrix.
+    Both algorithms then agree with the fp64 restatement to the conditioning-limited noise of fp32 and with each other;
+    on the reference's own weightings no row takes the fallback."""
+    if not tc_supported(f, False):
+        pytest.skip("shape not taken by the tcgen05 path")
+    C = make_counts(700, 500, 60_000, seed=11)
+    rng = np.random.default_rng(8)
+    C.data = (C.data * rng.uniform(500.0, 4000.0, size=C.nnz)).astype(np.float32)   # d up to 2e4
+    Y = orc.init_items(500, f, False)
+    ref = orc.half_step(Y, C, 0.1)
+    x64, tol = half_step_tol(Y, C, ref, False)
+    X, _ = run_half_step(Y, C, False, _lib.ALGO_TCGEN05, cuda_device)
+    fallback = engine.half_step_fallback_rows()
+    Xd, _ = run_half_step(Y, C, False, _lib.ALGO_TCGEN05_DIRECT, cuda_device)
+    assert np.all(np.isfinite(X)) and np.all(np.isfinite(Xd))
+    noise = row_rel_err(ref, x64)
+    e_cg, e_direct = row_rel_err(X, x64), row_rel_err(Xd, x64)
+    ledger_add(f"heavy_weights/f{f}", "tcgen05", err_vs_ref32=row_rel_err(X, ref), err_vs_fp64=e_cg, ref_noise=noise,
+               tol_vs_fp64=tol, tol_vs_ref32=None)
+    ledger_add(f"heavy_weights/f{f}", "tcgen05_direct", err_vs_ref32=row_rel_err(Xd, ref), err_vs_fp64=e_direct, ref_noise=noise,
+               tol_vs_fp64=tol, tol_vs_ref32=None)
+    print(f"heavy weights f={f}: {fallback} rows factorised; vs fp64: cg path {e_cg:.2e}, direct {e_direct:.2e}, "
+          f"reference {noise:.2e} (tol {tol:.1e})")
+    assert fallback > 0, "no row took the factorisation: the fallback is not exercised"
+    assert e_cg < tol and e_direct < tol
+    # the reference's weighting: nothing falls back
+    C2 = make_counts(700, 500, 60_000, seed=11)
+    C2.data = orc.preprocess_counts(C2.data)
+    run_half_step(Y, C2, False, _lib.ALGO_TCGEN05, cuda_device)
+    assert engine.half_step_fallback_rows() == 0
+
+
 def test_half_step_split_rows(cuda_device):
     """Rows longer than wmf_als_row_split_entries() are accumulated by several CTAs (tcgen05 path) and their
     partial Grams summed in segment order: same accuracy bar, bitwise independent of the schedule and of
