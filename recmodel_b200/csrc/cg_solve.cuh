@@ -104,7 +104,8 @@ __device__ __forceinline__ float cg_row_dot(uint32_t t_row, uint32_t vec, int W)
 //   vec   shared, W floats, 16-byte aligned: the vector being multiplied
 //   red   shared, 2 x nw x 2 floats, 8-byte aligned: warp partials of (r.r, r.Ar), double buffered by iteration
 __device__ __forceinline__ int cg_solve(uint32_t t_row, int t, int W, float b, float inv_s2, uint32_t vec, uint32_t red,
-                                        int wi, int nw, int bar, int nthr, int maxit, float& x_out) {
+                                        int wi, int nw, int bar, int nthr, int maxit, float& x_out,
+                                        long long* pf = nullptr) {   // pf: cycle counters of a profiling build
     const bool live = t < W;
     const int lane = threadIdx.x & 31;
     const bool solo = nw == 1;   // a single warp holds every row: no block barrier, no exchange through shared memory
@@ -113,10 +114,19 @@ __device__ __forceinline__ int cg_solve(uint32_t t_row, int t, int W, float b, f
     int products = -1;
 #pragma unroll 1
     for (int it = 0;; ++it) {
+#ifdef WMF_TC_PROFILE_BUILD
+        long long c0 = pf ? clock64() : 0, c1 = 0, c2 = 0, c3 = 0;
+#endif
         if (live) sts1(vec + (uint32_t)t * 4u, r);
         if (solo) __syncwarp(); else named_bar(bar, nthr);
+#ifdef WMF_TC_PROFILE_BUILD
+        if (pf) c1 = clock64();
+#endif
         float w = fmaf(cg_row_dot(t_row, vec, W), inv_s2, r);   // (A r)_t
         w = live ? w : 0.0f;
+#ifdef WMF_TC_PROFILE_BUILD
+        if (pf) { pf[3] += (long long)(__float_as_int(w) & 0); c2 = clock64(); }   // (the dependency keeps the clock behind the product)
+#endif
         float g = r * r, d = r * w;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {   // (every lane ends up with the warp's sums; the shuffles also order this
@@ -136,6 +146,9 @@ __device__ __forceinline__ int cg_solve(uint32_t t_row, int t, int W, float b, f
                 delta += q.y;
             }
         }
+#ifdef WMF_TC_PROFILE_BUILD
+        if (pf) { c3 = clock64() + (long long)(__float_as_int(gamma) & 0); pf[0] += c1 - c0; pf[1] += c2 - c1; pf[2] += c3 - c2; }
+#endif
         if (it == 0) gamma0 = gamma;
         if (gamma <= CG_TOL2 * gamma0) { products = it + 1; break; }   // also a zero right-hand side
         if (it >= maxit) break;

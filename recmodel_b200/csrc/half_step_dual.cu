@@ -305,7 +305,13 @@ als_half_step_dual_kernel(HalfStepParams p, const int4* __restrict__ dtab, const
             if (p.cg_maxit > 0) {
                 float xc = 0.0f;
                 int products = -1;
-                if (active) products = cg_solve(t_row, t, n16, bt, inv_s2, bfin, Dblk, qw, (n16 + 31) >> 5, CG_BAR0 + g, ((n16 + 31) >> 5) * 32, p.cg_maxit, xc);
+                if (active) products = cg_solve(t_row, t, n16, bt, inv_s2, bfin, Dblk, qw, (n16 + 31) >> 5, CG_BAR0 + g, ((n16 + 31) >> 5) * 32, p.cg_maxit, xc,
+#ifdef WMF_TC_PROFILE_BUILD
+                                                   prof ? p.prof + 52 : nullptr
+#else
+                                                   nullptr
+#endif
+                                                   );
 #ifdef WMF_TC_PROFILE_BUILD
                 if (prof) pf_prod += products;
 #endif

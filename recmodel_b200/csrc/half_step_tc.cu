@@ -741,7 +741,7 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
             if (p.cg_maxit > 0) {
                 float xc = 0.0f;
                 int products = -1;
-                if (active) products = cg_solve(t_row, t, f16, bt, inv_s2, bfin, Dblk, q, nact, CG_BAR0 + g, nact * 32, p.cg_maxit, xc);
+                if (active) products = cg_solve(t_row, t, f16, bt, inv_s2, bfin, Dblk, q, nact, CG_BAR0 + g, nact * 32, p.cg_maxit, xc, prof ? p.prof + 48 : nullptr);
                 const uint32_t flag = Dblk + 128u + (uint32_t)(my_rows & 1) * 4u;
                 if (t == 0) sts1(flag, products >= 0 ? 1.0f : 0.0f);
                 if (prof) { cg_rows += products >= 0; cg_products += products >= 0 ? products : p.cg_maxit + 1; }

@@ -29,6 +29,8 @@ def run(csr, Yd, name):
     print("  solver phases (thread 0 of group 0): wait_mma", f(prof[24]), "tmem_ld", f(prof[25]), "own_factor(4 of 16 panels)", f(prof[26]),
           "barA", f(prof[27]), "P", f(prof[28]), "split+sts+fence", f(prof[29]), "barB", f(prof[30]), "mma_issue", f(prof[31]))
     print("  cg: rows solved", prof[32], "of", prof[22], " products", prof[33])
+    print("  cg phases (thread 0, group 0), primal: publish+barrier", f(prof[48]), "product", f(prof[49]), "reduce", f(prof[50]),
+          "| dual: publish+barrier", f(prof[52]), "product", f(prof[53]), "reduce", f(prof[54]))
     if prof[44] > 0:
         print("  dual kernel, group 0 of CTA 0: total", f(prof[40]), "wait acc_full", f(prof[41]), "cg", f(prof[42]), "x'", f(prof[43]),
               "rows", prof[44], "products", prof[45], "entries", prof[46])
