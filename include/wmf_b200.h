@@ -141,11 +141,11 @@ int wmf_als_half_step(const int64_t* indptr, const int32_t* indices, const float
  * failed (row re-solved by the LU kernel), bit 3 G was not positive definite (all rows solved by the LU
  * kernel); *fixup_rows = rows the LU kernel solved. */
 int wmf_als_half_step_status(const void* ws, int* flags_host, int* fixup_rows_host, void* stream);
-/* Rows of the last WMF_ALGO_TCGEN05 call that used `ws` whose conjugate gradients did not reach the residual bound
- * within their product budget and were factorised in tensor memory instead (0 on the reference's weightings; weights
- * in the thousands get there). Replaces nothing in the reference (np.linalg.solve always factorises, wmf_model.py:239);
- * read after the stream has drained. */
-int wmf_als_half_step_fallback_rows(const void* ws, int* rows_host, void* stream);
+/* *any_row_host = 1 if, in the last WMF_ALGO_TCGEN05 call that used `ws`, the conjugate gradients of some row did not
+ * reach the residual bound within their product budget, so that the row was factorised in tensor memory instead (0 on
+ * the reference's weightings; weights in the thousands get there). Replaces nothing in the reference (np.linalg.solve
+ * always factorises, wmf_model.py:239); read after the stream has drained. */
+int wmf_als_half_step_used_fallback(const void* ws, int* any_row_host, void* stream);
 
 /* K3. Fused prediction + error reduction over the non-zero stored entries of a CSR matrix:
  * replaces predict + eval_prec (wmf_model.py:205-211, base_model.py:163-176).

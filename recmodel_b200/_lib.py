@@ -36,7 +36,7 @@ SIGNATURES = {
     "wmf_als_half_step_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "wmf_als_dual_max_entries": (_i32, []),
     "wmf_als_half_step_status": (_i32, [_p, _p, _p, _p]),
-    "wmf_als_half_step_fallback_rows": (_i32, [_p, _p, _p]),
+    "wmf_als_half_step_used_fallback": (_i32, [_p, _p, _p]),
     "wmf_als_half_step_supports": (_i32, [_i32, _i32, _i32]),
     "wmf_rank_ahead": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _p, _p]),
     "wmf_als_row_split_entries": (_i32, []),

@@ -50,9 +50,9 @@ int wmf_als_half_step_status(const void* ws, int* flags_host, int* fixup_rows_ho
     return WMF_OK;
 }
 
-int wmf_als_half_step_fallback_rows(const void* ws, int* rows_host, void* stream) {
-    WMF_REQUIRE(ws != nullptr && rows_host != nullptr, "wmf_als_half_step_fallback_rows: null pointer");
-    WMF_CUDA(cudaMemcpyAsync(rows_host, reinterpret_cast<const int*>(ws) + 12, sizeof(int), cudaMemcpyDeviceToHost,
+int wmf_als_half_step_used_fallback(const void* ws, int* any_row_host, void* stream) {
+    WMF_REQUIRE(ws != nullptr && any_row_host != nullptr, "wmf_als_half_step_used_fallback: null pointer");
+    WMF_CUDA(cudaMemcpyAsync(any_row_host, reinterpret_cast<const int*>(ws) + 12, sizeof(int), cudaMemcpyDeviceToHost,
                              (cudaStream_t)stream));
     WMF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return WMF_OK;

@@ -753,7 +753,10 @@ als_half_step_tc_kernel(const __grid_constant__ CUtensorMap ymap, HalfStepParams
                     if (prof) t_fact += clock64() - tt;
                     continue;
                 }
-                if (t == 0) atomicAdd(flags + 11, 1);   // header word 12: rows the factorisation had to take
+                                // header word 12: some row took the factorisation (a plain store: an atomicAdd at this point made the
+                // whole kernel 50 % slower, measured A/B on one box, although it never executes on the bench workloads)
+                if (t == 0) *reinterpret_cast<volatile int*>(flags + 11) = 1;
+
                 tc_fence_after();
             }
 #pragma unroll 1
@@ -942,8 +945,8 @@ bool tc_half_step_supported(int f, int bias) { return f >= 1 && f <= 256 && (!bi
 // Workspace (bytes from a 256-aligned base):
 //   [0, 1024)   header: [1] flags (1 unused, 2 failed pivot, 8 G not positive definite), [2] max y~^2 (float bits),
 //               [4] total slots, [5] split rows, [6] partial slots, [7] extra slots, [8] fix-up rows, [9] end of the
-//               primal rows' slots, [10] 0x7fffffff - first dual slot, [11] end of the dual rows' slots, [12] rows whose
-//               conjugate gradients did not converge (factorised instead); [256, 768) profile
+//               primal rows' slots, [10] 0x7fffffff - first dual slot, [11] end of the dual rows' slots, [12] nonzero when the
+//               conjugate gradients of some row did not converge (factorised instead); [256, 768) profile
 //   tables      primal row table + split table (32 B per slot), dual row table (16 B per slot), split-row counters,
 //               fix-up list (4 B per row)
 //   whitening   double scratch of the Cholesky, the two FP x FP multipliers, Y~ (cols x FP), X' (rows x FP)

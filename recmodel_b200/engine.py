@@ -426,21 +426,21 @@ def half_step_status(ws=None):
     return flags.value, fixed.value
 
 
-def half_step_fallback_rows(ws=None):
-    """Rows of the last tcgen05 half-step that used ``ws`` whose conjugate gradients did not converge within their
-    product budget and were factorised in tensor memory instead (synchronises the stream)."""
+def half_step_used_fallback(ws=None):
+    """True if some row of the last tcgen05 half-step that used ``ws`` was factorised in tensor memory because its
+    conjugate gradients did not converge within their product budget (synchronises the stream)."""
     import ctypes
     lib = _lib.load()
     if ws is None:
         ref = getattr(half_step, "last_ws", None)
         ws = ref() if ref is not None else None
     if ws is None:
-        return 0
+        return False
     rows = ctypes.c_int(0)
     with _on(ws.device):
-        _lib.check(lib.wmf_als_half_step_fallback_rows(_ptr(ws), ctypes.addressof(rows), _stream(ws.device)),
-                   "wmf_als_half_step_fallback_rows")
-    return rows.value
+        _lib.check(lib.wmf_als_half_step_used_fallback(_ptr(ws), ctypes.addressof(rows), _stream(ws.device)),
+                   "wmf_als_half_step_used_fallback")
+    return rows.value != 0
 
 
 @_device_of(1)

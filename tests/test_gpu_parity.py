@@ -279,7 +279,7 @@ def test_half_step_cg_falls_back_to_factorisation(cuda_device, f):
     ref = orc.half_step(Y, C, 0.1)
     x64, tol = half_step_tol(Y, C, ref, False)
     X, _ = run_half_step(Y, C, False, _lib.ALGO_TCGEN05, cuda_device)
-    fallback = engine.half_step_fallback_rows()
+    fallback = engine.half_step_used_fallback()
     Xd, _ = run_half_step(Y, C, False, _lib.ALGO_TCGEN05_DIRECT, cuda_device)
     assert np.all(np.isfinite(X)) and np.all(np.isfinite(Xd))
     noise = row_rel_err(ref, x64)
@@ -288,15 +288,15 @@ def test_half_step_cg_falls_back_to_factorisation(cuda_device, f):
                tol_vs_fp64=tol, tol_vs_ref32=None)
     ledger_add(f"heavy_weights/f{f}", "tcgen05_direct", err_vs_ref32=row_rel_err(Xd, ref), err_vs_fp64=e_direct, ref_noise=noise,
                tol_vs_fp64=tol, tol_vs_ref32=None)
-    print(f"heavy weights f={f}: {fallback} rows factorised; vs fp64: cg path {e_cg:.2e}, direct {e_direct:.2e}, "
+    print(f"heavy weights f={f}: factorisation used: {fallback}; vs fp64: cg path {e_cg:.2e}, direct {e_direct:.2e}, "
           f"reference {noise:.2e} (tol {tol:.1e})")
-    assert fallback > 0, "no row took the factorisation: the fallback is not exercised"
+    assert fallback, "no row took the factorisation: the fallback is not exercised"
     assert e_cg < tol and e_direct < tol
     # the reference's weighting: nothing falls back
     C2 = make_counts(700, 500, 60_000, seed=11)
     C2.data = orc.preprocess_counts(C2.data)
     run_half_step(Y, C2, False, _lib.ALGO_TCGEN05, cuda_device)
-    assert engine.half_step_fallback_rows() == 0
+    assert not engine.half_step_used_fallback()
 
 
 def test_half_step_split_rows(cuda_device):
