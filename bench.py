@@ -34,6 +34,8 @@ WORKLOADS = {
     "netflix": (480_189, 17_770, 100_000_000, 128, "device", "configs[2]: Netflix shape"),
     "powerlaw256": (1_000_000, 100_000, 100_000_000, 256, "device",
                     "configs[3] at 1/10 of every dimension (the 10 M x 1 M, 1 B-entry matrix needs 8 GPUs)"),
+    "powerlaw1b": (10_000_000, 1_000_000, 1_000_000_000, 256, "device",
+                   "configs[3]: power-law 10 M x 1 M, 1 B entries, dim 256 (row-sharded; needs several GPUs)"),
     "rank": (138_493, 26_744, 20_000_000, 128, "host", "configs[4]: top-100 for all users, ML-20M shape"),
     "ml1m": (6040, 3706, 1_000_000, 64, "host", "debugging only; never the reported config"),
 }
@@ -235,6 +237,19 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def pin_csr(m):
+    """The same scipy CSR matrix with its three arrays in page-locked host memory (NumPy views of pinned torch
+    tensors): WMF.train then DMAs straight out of them instead of staging a copy."""
+    import scipy.sparse
+    import torch
+
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    out = scipy.sparse.csr_matrix((pin(m.data), pin(m.indices), pin(m.indptr)), shape=m.shape, copy=False)
+    out.has_sorted_indices = m.has_sorted_indices
+    return out
+
+
 def make_device_matrix(workload, device):
     """(DeviceCSR of raw counts, host CSR or None). Host-generated workloads are uploaded; the large ones are
     generated on the device with the same recipe."""
@@ -448,6 +463,8 @@ def run_ours(args):
                                               C_full.indptr.cpu().numpy()), shape=(users, items))
         del C_full, CT_full, raw_counts
         tr_host, te_host = split_train_test(C_host, train=0.8, seed=1993)
+        if not args.pageable:
+            tr_host, te_host = pin_csr(tr_host), pin_csr(te_host)   # the contract's e2e inputs: pinned host memory
         e2e_steps = max(1, min(args.steps, 5))
 
         def e2e_step():
@@ -529,8 +546,9 @@ def run_ours(args):
                     "host_marks_ms_per_step": marks,
                     "device_ms_last_step": {"half_steps": model.last_train_stats.get("half_step_ms"),
                                             "eval": model.last_train_stats.get("eval_ms")},
-                    "what": "WMF.train(host CSR, iterations=1) incl. upload, preprocess, transpose, epoch, eval_prec, "
-                            "factor read-back; 80/20 split so nnz = train nnz"},
+                    "what": "WMF.train(host CSR in " + ("pageable" if args.pageable else "pinned") + " host memory, iterations=1) "
+                            "incl. upload, preprocess, transpose, epoch, eval_prec, factor read-back; 80/20 split so nnz = "
+                            "train nnz"},
             "gpu_launches": int(launches_per_epoch * args.steps),
             "gpu_launches_note": f"{launches_per_epoch} kernel launches of libwmf_b200.so per epoch, counted by the library "
                                  "(wmf_launch_count) while the epoch was captured, x steps",
@@ -564,6 +582,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="ml20m")
     ap.add_argument("--algo", choices=["auto", "simt", "tcgen05", "tcgen05_direct"], default="auto")
+    ap.add_argument("--pageable", action="store_true",
+                    help="e2e: hand WMF.train ordinary (pageable) NumPy arrays instead of pinned ones (adds the staging copy)")
     ap.add_argument("--cpu-frac", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel tuning runs: skip the end-to-end leg (the line's e2e is NaN)")

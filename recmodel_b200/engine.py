@@ -89,6 +89,10 @@ def _h2d(arr, dtype, device):
     n = t.numel()
     if a.nbytes < (4 << 20) or device.type != "cuda":
         return t.to(device, non_blocking=True)
+    if t.is_pinned():
+        # the caller's array already lives in page-locked memory (and needed no dtype conversion): DMA straight out
+        # of it; the staging copy below exists only to give pageable arrays that property
+        return t.to(device, non_blocking=True)
     key = (t.dtype, device.index)
     ent = _pinned.get(key)
     if ent is None or ent[0].numel() < n:
