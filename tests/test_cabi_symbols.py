@@ -30,6 +30,40 @@ def test_header_and_binding_agree(lib):
         assert hasattr(lib, n), f"{n} declared in the header but not exported by libwmf_b200.so"
 
 
+def header_arity(name):
+    """Number of parameters of `name` in include/wmf_b200.h (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "wmf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert m, name
+    args = m.group(1).strip()
+    return 0 if args in ("", "void") else args.count(",") + 1
+
+
+def test_binding_arity_matches_the_header():
+    """Every ctypes signature has as many arguments as the declaration in the header (a drifted binding would pass
+    garbage to a kernel), and the algorithm selectors of the binding are the header's."""
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert header_arity(name) == len(argtypes), f"{name}: header and recmodel_b200/_lib.py disagree on the argument count"
+    text = open(os.path.join(ROOT, "include", "wmf_b200.h")).read()
+    for macro, value in (("WMF_ALGO_AUTO", _lib.ALGO_AUTO), ("WMF_ALGO_SIMT", _lib.ALGO_SIMT),
+                         ("WMF_ALGO_TCGEN05", _lib.ALGO_TCGEN05), ("WMF_ALGO_TCGEN05_DIRECT", _lib.ALGO_TCGEN05_DIRECT)):
+        m = re.search(r"#define\s+" + macro + r"\s+(\d+)", text)
+        assert m and int(m.group(1)) == value, macro
+
+
+def test_integration_example_matches_the_header():
+    """INTEGRATION.md's reference-side ctypes stub declares wmf_als_half_step and its workspace query with the header's
+    argument counts."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in ("wmf_als_half_step", "wmf_als_half_step_workspace_bytes", "wmf_gram", "wmf_gram_workspace_bytes"):
+        m = re.search(r"_lib\." + name + r"\.argtypes\s*=\s*(.*?)\n(?=_lib\.|\n|def )", doc, flags=re.S)
+        assert m, f"{name}: no argtypes in INTEGRATION.md"
+        expr = m.group(1)
+        ns = {"ctypes": ctypes}
+        assert len(eval(expr, ns)) == header_arity(name), f"{name}: INTEGRATION.md and the header disagree"
+
+
 def test_version_and_error_string(lib):
     assert lib.wmf_version() >= 100
     assert isinstance(_lib.last_error(), str)
