@@ -150,3 +150,25 @@ def test_utils_mirror_reference_semantics():
         cand = np.delete(np.arange(40), seen)
         want[cand[np.argsort(-scores[u, cand], kind="stable")][:5]] += 1
     np.testing.assert_array_equal(got, want)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU and prints exactly one JSON
+    line with the contract's keys: same metric / unit / config as our arm, `impl`, a `cpu_baseline` that describes
+    the run and an `e2e` object without copies."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ml1m",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "wmf_nnz_updates_per_sec_per_epoch" and d["unit"] == "nnz-updates/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["config"]["workload"].startswith("WMF weighted ALS epoch, 6040x3706") and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["gpu_launches"] == 0
