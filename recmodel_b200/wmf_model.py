@@ -157,13 +157,17 @@ class WMF(RecModel):
             ids = ids[:len(users)]
         elif k <= _lib.TOPK_MAX:
             ids = engine.score_topk(users_d, cand_d, U, V, k, bias=self.bias is True)
-        else:  # very long lists: exact device scores, then a stable device sort (ties by position)
+        else:  # very long lists: exact device scores, then a stable device sort (ties by position), many users per pass
             rows = []
-            for u in users_d:
-                s = engine.predict_pairs(u.reshape(1), cand_d, U, V, bias=self.bias is True)
-                order = torch.sort(s, descending=True, stable=True).indices[:k]
+            per = max(1, (1 << 24) // ni)   # at most ~16 M (user, candidate) pairs in flight
+            for u0 in range(0, users_d.numel(), per):
+                chunk = users_d[u0:u0 + per]
+                pu = chunk.repeat_interleave(ni)
+                pi = cand_d.repeat(chunk.numel())
+                s = engine.predict_pairs(pu, pi, U, V, bias=self.bias is True).view(chunk.numel(), ni)
+                order = torch.sort(s, dim=1, descending=True, stable=True).indices[:, :k]
                 rows.append(cand_d[order])
-            ids = torch.stack(rows)
+            ids = torch.cat(rows) if rows else torch.empty((0, k), dtype=torch.int64, device=self.device)
         return ids.cpu().numpy().astype(items.dtype, copy=False)
 
     # ---------------------------------------------------------------- train (R2, R7, R11)
